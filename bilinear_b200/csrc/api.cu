@@ -1,0 +1,806 @@
+// C ABI (include/bilinear_b200.h) + plan builder: carves the caller's workspace, encodes the TMA
+// tensor maps and lays out the phase schedules that mega.cu executes.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/bilinear_b200.h"
+#include "jobs.h"
+
+namespace b200 {
+cudaError_t launch_mega(const MegaParams& p, int grid, bool cooperative, cudaStream_t stream);
+int mega_ring_bytes();
+struct EvalParams {
+  const float* pred; const float* gt; const float* mean; const float* stddev; const int32_t* action;
+  float* dist_out; float* pdist_out; double* acc_sum; double* pacc_sum; long long* acc_cnt;
+  int64_t n; int32_t n_actions;
+};
+cudaError_t launch_eval(const EvalParams& prm, int joints, bool do_m, bool do_p, cudaStream_t stream);
+}  // namespace b200
+
+using namespace b200;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CK(expr)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 plane tensor viewed as {inner, rows, planes}; box {64 inner elements (128 B), box_rows, 1};
+// 128-byte swizzle; out-of-bounds elements read as zero (ragged batch / K tails / 48-row decode).
+static int encode_map(CUtensorMap* out, const void* base, int64_t inner, int64_t rows, int planes, int64_t ld,
+                      int64_t plane_stride, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  if (planes == 1) plane_stride = std::max<int64_t>(plane_stride, rows * ld);
+  cuuint64_t dims[3] = {cuuint64_t(inner), cuuint64_t(rows), cuuint64_t(planes)};
+  cuuint64_t strides[2] = {cuuint64_t(ld) * 2, cuuint64_t(plane_stride) * 2};
+  cuuint32_t box[3] = {64, cuuint32_t(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if ((strides[0] % 16) || (strides[1] % 16) || (reinterpret_cast<uintptr_t>(base) % 16))
+    return fail("tensor map alignment: ld=%lld plane_stride=%lld base=%p", (long long)ld, (long long)plane_stride, base);
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled -> %d (inner=%lld rows=%lld planes=%d ld=%lld box_rows=%d)", int(r),
+                (long long)inner, (long long)rows, planes, (long long)ld, box_rows);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat parameter layout (order of BilinearUnit.parameters(), model/bilinear.py:22-29)
+// ------------------------------------------------------------------------------------------------
+struct ParamLayout {
+  int64_t w[kNumLinear], b[kNumLinear], g[kNumHeavy], be[kNumHeavy];
+  int rows[kNumLinear], cols[kNumLinear];
+  int64_t numel;
+  ParamLayout() {
+    int64_t o = 0;
+    for (int l = 0; l < kNumLinear; ++l) {
+      rows[l] = (l == 5) ? kDout : kHidden;
+      cols[l] = (l == 0) ? kDin : kHidden;
+      w[l] = o; o += int64_t(rows[l]) * cols[l];
+      b[l] = o; o += rows[l];
+      if (l < kNumHeavy) { g[l] = o; o += kHidden; be[l] = o; o += kHidden; }
+    }
+    numel = o;
+  }
+};
+static const ParamLayout kPL;
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving
+// ------------------------------------------------------------------------------------------------
+struct Carver {
+  uint8_t* base;
+  int64_t off = 0;
+  explicit Carver(void* b) : base(reinterpret_cast<uint8_t*>(b)) {}
+  void* take(int64_t bytes) {
+    off = (off + 1023) & ~int64_t(1023);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+  template <class T> T* take_n(int64_t n) { return reinterpret_cast<T*>(take(n * int64_t(sizeof(T)))); }
+};
+
+constexpr int kMaxTmaps = 128, kMaxGemm = 64, kMaxEw = 64, kMaxPhases = 128;
+
+struct Bufs {
+  CUtensorMap* tmaps; GemmJob* gjobs; EwJob* ejobs; Phase* phases; unsigned int* barrier;
+  uint8_t* acc_base; int64_t acc_bytes;
+  double* loss_acc; double* gnorm2; double* stats_f[kNumHeavy]; double* stats_b[kNumHeavy];
+  float* save_mean[kNumHeavy]; float* save_rstd[kNumHeavy]; float* scale[kNumHeavy]; float* shift[kNumHeavy];
+  PlaneRef W[kNumLinear], WT[kNumLinear];
+  PlaneRef X_bm, X_fm;
+  void* zT[kNumHeavy]; void* dyT[kNumHeavy];
+  uint32_t* keep[kNumHeavy]; uint32_t* drop;
+  PlaneRef h_bm[kNumHeavy], h_fm[kNumHeavy], dz_bm[kNumHeavy], dz_fm[kNumHeavy];
+  float* G2; float* G4;
+  PlaneRef dP_bm, dP_fm;
+  int64_t Bs, ldw;
+};
+
+static PlaneRef take_planes(Carver& c, int planes, int64_t rows, int64_t ld) {
+  PlaneRef r;
+  const int64_t ps = (rows * ld + 511) & ~int64_t(511);
+  r.p = c.take_n<uint16_t>(ps * planes);
+  r.plane_stride = ps;
+  r.ld = ld;
+  return r;
+}
+
+static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
+  const bool train = (kind == B200_PLAN_TRAIN);
+  const bool large = B > (P == 1 ? 256 : 128);
+  const int64_t Bs = (int64_t(B) + 31) & ~int64_t(31);
+  const int64_t ldw = Bs / 32;
+  u.Bs = Bs; u.ldw = ldw;
+  u.tmaps = c.take_n<CUtensorMap>(kMaxTmaps);
+  u.gjobs = c.take_n<GemmJob>(kMaxGemm);
+  u.ejobs = c.take_n<EwJob>(kMaxEw);
+  u.phases = c.take_n<Phase>(kMaxPhases);
+  u.barrier = c.take_n<unsigned int>(64);
+  // accumulators cleared at the start of every step (one contiguous region)
+  const int64_t acc0 = (c.off + 1023) & ~int64_t(1023);
+  u.loss_acc = c.take_n<double>(16);
+  u.gnorm2 = u.loss_acc ? u.loss_acc + 8 : nullptr;
+  for (int l = 0; l < kNumHeavy; ++l) u.stats_f[l] = c.take_n<double>(2 * kHidden);
+  for (int l = 0; l < kNumHeavy; ++l) u.stats_b[l] = c.take_n<double>(2 * kHidden);
+  c.take(0);
+  u.acc_base = c.base ? c.base + acc0 : nullptr;
+  u.acc_bytes = ((c.off + 1023) & ~int64_t(1023)) - acc0;
+  for (int l = 0; l < kNumHeavy; ++l) {
+    u.save_mean[l] = c.take_n<float>(kHidden); u.save_rstd[l] = c.take_n<float>(kHidden);
+    u.scale[l] = c.take_n<float>(kHidden); u.shift[l] = c.take_n<float>(kHidden);
+  }
+  for (int l = 0; l < kNumLinear; ++l) {
+    u.W[l] = take_planes(c, P, kPL.rows[l], kPL.cols[l]);
+    if (train && l >= 1) u.WT[l] = take_planes(c, P, kPL.cols[l], kPL.rows[l]);
+    else u.WT[l] = PlaneRef{nullptr, 0, 0};
+  }
+  u.X_bm = take_planes(c, P, B, kDin);
+  u.X_fm = train ? take_planes(c, P, kDin, Bs) : PlaneRef{nullptr, 0, 0};
+  const int64_t zbytes = int64_t(kHidden) * Bs * (P == 1 ? 2 : 4);
+  u.drop = train ? c.take_n<uint32_t>(int64_t(kNumHeavy) * kHidden * ldw) : nullptr;
+  for (int l = 0; l < kNumHeavy; ++l) {
+    u.h_bm[l] = take_planes(c, P, B, kHidden);
+    u.h_fm[l] = (train || l == 0 || l == 2) ? take_planes(c, P, kHidden, Bs) : PlaneRef{nullptr, 0, 0};
+    if (train) {
+      u.zT[l] = c.take(zbytes);
+      u.dyT[l] = large ? c.take(zbytes) : nullptr;
+      u.keep[l] = c.take_n<uint32_t>(int64_t(kHidden) * ldw);
+      u.dz_bm[l] = take_planes(c, P, B, kHidden);
+      u.dz_fm[l] = take_planes(c, P, kHidden, Bs);
+    } else {
+      u.zT[l] = u.dyT[l] = nullptr; u.keep[l] = nullptr;
+      u.dz_bm[l] = u.dz_fm[l] = PlaneRef{nullptr, 0, 0};
+    }
+  }
+  if (train) {
+    u.G2 = c.take_n<float>(int64_t(kHidden) * Bs);
+    u.G4 = c.take_n<float>(int64_t(kHidden) * Bs);
+    u.dP_bm = take_planes(c, P, B, kDout);
+    u.dP_fm = take_planes(c, P, kDout, Bs);
+  } else {
+    u.G2 = u.G4 = nullptr;
+    u.dP_bm = u.dP_fm = PlaneRef{nullptr, 0, 0};
+  }
+  c.take(0);
+  return c.off + 1024;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct Sched { int first = 0, count = 0; };
+
+struct b200_plan {
+  b200_plan_desc d;
+  Bufs u;
+  int B, P, kind;
+  bool large;
+  int sms;
+  std::vector<CUtensorMap> tm;
+  std::vector<GemmJob> gj;
+  std::vector<EwJob> ej;
+  std::vector<Phase> ph;
+  Sched s_refresh, s_eval, s_fwd, s_bwd, s_step, s_update;
+  bool phase_open = false;
+  Phase cur;
+};
+
+static int add_map(b200_plan* pl, const PlaneRef& r, int64_t inner, int64_t rows, int box_rows, int* idx) {
+  if (int(pl->tm.size()) >= kMaxTmaps) return fail("too many tensor maps");
+  CUtensorMap m;
+  if (encode_map(&m, r.p, inner, rows, pl->P, r.ld, r.plane_stride, box_rows)) return 1;
+  pl->tm.push_back(m);
+  *idx = int(pl->tm.size()) - 1;
+  return 0;
+}
+
+static void begin_phase(b200_plan* pl) {
+  pl->cur = Phase{};
+  pl->cur.first_gemm = int(pl->gj.size());
+  pl->cur.first_ew = int(pl->ej.size());
+  pl->cur.stage_bytes = 1024;
+  pl->cur.num_stages = 1;
+}
+static void end_phase(b200_plan* pl) {
+  Phase& p = pl->cur;
+  p.num_gemm = int(pl->gj.size()) - p.first_gemm;
+  p.num_ew = int(pl->ej.size()) - p.first_ew;
+  p.gemm_tiles = 0;
+  int sb = 1024;
+  for (int j = 0; j < p.num_gemm; ++j) {
+    const GemmJob& g = pl->gj[p.first_gemm + j];
+    p.gemm_tiles += g.num_tiles;
+    sb = std::max(sb, g.a.planes * (128 * 128 + g.BN * 128));
+  }
+  p.stage_bytes = sb;
+  p.num_stages = std::max(1, std::min(8, mega_ring_bytes() / sb));
+  pl->ph.push_back(p);
+}
+
+static Args base_args(const b200_plan* pl, int layer) {
+  Args a;
+  memset(&a, 0, sizeof a);
+  a.layer = layer;
+  a.planes = pl->P;
+  a.B = pl->B;
+  a.ldT = pl->u.Bs;
+  a.ldw = pl->u.ldw;
+  return a;
+}
+
+static int add_gemm(b200_plan* pl, const PlaneRef& A, int64_t a_inner, int64_t a_rows, const PlaneRef& Bop,
+                    int64_t b_inner, int64_t b_rows, int M, int N, int K, int BN, int epi, const Args& a) {
+  if (int(pl->gj.size()) >= kMaxGemm) return fail("too many gemm jobs");
+  GemmJob g;
+  memset(&g, 0, sizeof g);
+  if (add_map(pl, A, a_inner, a_rows, 128, &g.tmap_a)) return 1;
+  if (add_map(pl, Bop, b_inner, b_rows, BN, &g.tmap_b)) return 1;
+  g.M = M; g.N = N; g.K = K; g.BN = BN;
+  g.m_tiles = (M + 127) / 128;
+  g.n_tiles = (N + BN - 1) / BN;
+  g.num_tiles = g.m_tiles * g.n_tiles;
+  g.epi = epi;
+  g.a = a;
+  pl->gj.push_back(g);
+  return 0;
+}
+static int add_ew(b200_plan* pl, int kind, const Args& a) {
+  if (int(pl->ej.size()) >= kMaxEw) return fail("too many elementwise jobs");
+  EwJob e;
+  memset(&e, 0, sizeof e);
+  e.kind = kind;
+  e.a = a;
+  pl->ej.push_back(e);
+  return 0;
+}
+
+static Args adam_args(const b200_plan* pl) {
+  Args a = base_args(pl, 0);
+  a.params = pl->d.params; a.grads = pl->d.grads; a.exp_avg = pl->d.exp_avg; a.exp_avg_sq = pl->d.exp_avg_sq;
+  a.numel = kPL.numel;
+  a.gnorm2 = pl->u.gnorm2;
+  a.loss_acc = pl->u.loss_acc;
+  for (int l = 0; l < kNumLinear; ++l) {
+    a.w_off[l] = kPL.w[l]; a.w_rows[l] = kPL.rows[l]; a.w_cols[l] = kPL.cols[l];
+    a.w_planes[l] = pl->u.W[l];
+    a.wT_planes[l] = pl->u.WT[l];
+  }
+  return a;
+}
+
+static int tile_bn(const b200_plan* pl, int n) {
+  const int cap = (pl->P == 1) ? 256 : 128;
+  const int r = (n + 15) & ~15;
+  return std::min(cap, r);
+}
+
+// forward heavy layer l (model/bilinear.py:7-13) -- train or eval flavour
+static int build_fwd_layer(b200_plan* pl, int l, bool train) {
+  const Bufs& u = pl->u;
+  const b200_plan_desc& d = pl->d;
+  const int B = pl->B;
+  Args a = base_args(pl, l);
+  a.bias = d.params + kPL.b[l];
+  a.gamma = d.params + kPL.g[l];
+  a.beta = d.params + kPL.be[l];
+  a.run_mean = d.running_mean[l]; a.run_var = d.running_var[l]; a.nbt = d.num_batches_tracked[l];
+  a.save_mean = u.save_mean[l]; a.save_rstd = u.save_rstd[l];
+  a.scale = u.scale[l]; a.shift = u.shift[l];
+  a.stats = u.stats_f[l];
+  a.zT = u.zT[l];
+  a.keep = u.keep[l];
+  a.drop = u.drop ? u.drop + int64_t(l) * kHidden * u.ldw : nullptr;
+  if (l == 2) a.skip_fm = u.h_fm[0];
+  if (l == 4) a.skip_fm = u.h_fm[2];
+  a.out_bm = u.h_bm[l];
+  a.out_fm = u.h_fm[l];
+  const PlaneRef& in = (l == 0) ? u.X_bm : u.h_bm[l - 1];
+  const int K = kPL.cols[l];
+  const int BN = tile_bn(pl, B);
+  const int epi = !train ? EPI_FWD_EVAL : (pl->large ? EPI_FWD_LARGE : EPI_FWD_SMALL);
+  begin_phase(pl);
+  if (add_gemm(pl, u.W[l], K, kHidden, in, K, B, kHidden, B, K, BN, epi, a)) return 1;
+  end_phase(pl);
+  if (train && pl->large) {
+    begin_phase(pl);
+    if (add_ew(pl, EW_BN_FWD_APPLY, a)) return 1;
+    end_phase(pl);
+  }
+  return 0;
+}
+
+static int build_decode(b200_plan* pl, bool fuse_loss) {
+  const Bufs& u = pl->u;
+  Args a = base_args(pl, 5);
+  a.bias = pl->d.params + kPL.b[5];
+  a.fuse_loss = fuse_loss ? 1 : 0;
+  a.loss_acc = u.loss_acc;
+  a.grad_bias = pl->d.grads ? pl->d.grads + kPL.b[5] : nullptr;
+  a.out_bm = u.dP_bm;
+  a.out_fm = u.dP_fm;
+  begin_phase(pl);
+  if (add_gemm(pl, u.W[5], kHidden, kDout, u.h_bm[4], kHidden, pl->B, kDout, pl->B, kHidden, tile_bn(pl, pl->B),
+               EPI_DECODE, a))
+    return 1;
+  end_phase(pl);
+  return 0;
+}
+
+// backward phases (autograd of model/bilinear.py:31-41): for l = 4..0 { dgrad(l+1 -> l) with the
+// BN/ReLU/dropout backward of layer l in its epilogue, wgrad(l+1) } then wgrad(0).
+static int build_backward(b200_plan* pl, bool with_norm) {
+  const Bufs& u = pl->u;
+  const b200_plan_desc& d = pl->d;
+  const int B = pl->B;
+  for (int l = 4; l >= 0; --l) {
+    Args a = base_args(pl, l);
+    a.gamma = d.params + kPL.g[l];
+    a.save_mean = u.save_mean[l]; a.save_rstd = u.save_rstd[l];
+    a.zT = u.zT[l]; a.dyT = u.dyT[l];
+    a.keep = u.keep[l];
+    a.stats = u.stats_b[l];
+    a.skip_in = (l == 2) ? u.G4 : (l == 0 ? u.G2 : nullptr);
+    a.g_out = (l == 4) ? u.G4 : (l == 2 ? u.G2 : nullptr);
+    a.out_bm = u.dz_bm[l];
+    a.out_fm = u.dz_fm[l];
+    a.grad_bias = d.grads + kPL.b[l];
+    a.grad_gamma = d.grads + kPL.g[l];
+    a.grad_beta = d.grads + kPL.be[l];
+    a.gnorm2 = with_norm ? u.gnorm2 : nullptr;
+    const int up = l + 1;                      // the Linear whose input is h_l
+    const int Kd = kPL.rows[up];               // 1024, or 48 for decode
+    const PlaneRef& dzu = (up == 5) ? u.dP_bm : u.dz_bm[up];
+    begin_phase(pl);
+    if (add_gemm(pl, u.WT[up], Kd, kHidden, dzu, Kd, B, kHidden, B, Kd, tile_bn(pl, B),
+                 pl->large ? EPI_DGRAD_LARGE : EPI_DGRAD_SMALL, a))
+      return 1;
+    {  // wgrad of Linear `up`: dW[out][in] = sum_b dz[b][out] h_l[b][in]
+      Args w = base_args(pl, up);
+      w.out_f32 = d.grads + kPL.w[up];
+      w.ld_out = kHidden;
+      w.gnorm2 = with_norm ? u.gnorm2 : nullptr;
+      const PlaneRef& dzT = (up == 5) ? u.dP_fm : u.dz_fm[up];
+      if (add_gemm(pl, dzT, B, kPL.rows[up], u.h_fm[l], B, kHidden, kPL.rows[up], kHidden, B, tile_bn(pl, kHidden),
+                   EPI_WGRAD, w))
+        return 1;
+    }
+    end_phase(pl);
+    if (pl->large) {
+      begin_phase(pl);
+      if (add_ew(pl, EW_BN_BWD_APPLY, a)) return 1;
+      end_phase(pl);
+    }
+  }
+  begin_phase(pl);
+  {
+    Args w = base_args(pl, 0);
+    w.out_f32 = d.grads + kPL.w[0];
+    w.ld_out = kDin;
+    w.gnorm2 = with_norm ? u.gnorm2 : nullptr;
+    if (add_gemm(pl, u.dz_fm[0], B, kHidden, u.X_fm, B, kDin, kHidden, kDin, B, 32, EPI_WGRAD, w)) return 1;
+  }
+  end_phase(pl);
+  return 0;
+}
+
+static void zero_list_step(const b200_plan* pl, Args& a, bool fwd_acc, bool bwd_grads) {
+  int k = 0;
+  if (fwd_acc) { a.zero_ptr[k] = pl->u.acc_base; a.zero_bytes[k] = pl->u.acc_bytes; ++k; }
+  if (bwd_grads) {
+    // gradient slots that are accumulated with atomics: decode bias always, heavy biases on the large path
+    a.zero_ptr[k] = pl->d.grads + kPL.b[5]; a.zero_bytes[k] = kDout * 4; ++k;
+    if (pl->large)
+      for (int l = 0; l < kNumHeavy; ++l) { a.zero_ptr[k] = pl->d.grads + kPL.b[l]; a.zero_bytes[k] = kHidden * 4; ++k; }
+  }
+}
+
+static int build_plan(b200_plan* pl) {
+  const Bufs& u = pl->u;
+  const b200_plan_desc& d = pl->d;
+  const bool train = pl->kind == B200_PLAN_TRAIN;
+
+  // ---- refresh: master weights -> operand planes
+  pl->s_refresh.first = int(pl->ph.size());
+  begin_phase(pl);
+  if (add_ew(pl, EW_SPLIT_W, adam_args(pl))) return 1;
+  end_phase(pl);
+  pl->s_refresh.count = int(pl->ph.size()) - pl->s_refresh.first;
+
+  // ---- eval forward (valid_bilinear.py:52)
+  pl->s_eval.first = int(pl->ph.size());
+  begin_phase(pl);
+  for (int l = 0; l < kNumHeavy; ++l) {
+    Args a = base_args(pl, l);
+    a.bias = d.params + kPL.b[l]; a.gamma = d.params + kPL.g[l]; a.beta = d.params + kPL.be[l];
+    a.run_mean = d.running_mean[l]; a.run_var = d.running_var[l];
+    a.scale_w = u.scale[l]; a.shift_w = u.shift[l];
+    if (add_ew(pl, EW_BN_FOLD, a)) return 1;
+  }
+  {
+    Args a = base_args(pl, 0);
+    a.src = SRC_X; a.src_cols = kDin; a.out_bm = u.X_bm;
+    if (add_ew(pl, EW_PREP, a)) return 1;
+  }
+  end_phase(pl);
+  for (int l = 0; l < kNumHeavy; ++l)
+    if (build_fwd_layer(pl, l, false)) return 1;
+  if (build_decode(pl, false)) return 1;
+  pl->s_eval.count = int(pl->ph.size()) - pl->s_eval.first;
+  if (!train) return 0;
+
+  auto prep_fwd = [&](bool zero_grads) -> int {
+    begin_phase(pl);
+    Args a = base_args(pl, 0);
+    a.src = SRC_X; a.src_cols = kDin; a.out_bm = u.X_bm; a.out_fm = u.X_fm;
+    zero_list_step(pl, a, true, zero_grads);
+    for (int l = 0; l < kNumHeavy; ++l) a.nbt_w[l] = d.num_batches_tracked[l];
+    if (add_ew(pl, EW_PREP, a)) return 1;
+    Args b = base_args(pl, 0);
+    b.keep = u.drop;
+    if (add_ew(pl, EW_DROPBITS, b)) return 1;
+    end_phase(pl);
+    return 0;
+  };
+
+  // ---- training-mode forward alone (autograd path)
+  pl->s_fwd.first = int(pl->ph.size());
+  if (prep_fwd(false)) return 1;
+  for (int l = 0; l < kNumHeavy; ++l)
+    if (build_fwd_layer(pl, l, true)) return 1;
+  if (build_decode(pl, false)) return 1;
+  pl->s_fwd.count = int(pl->ph.size()) - pl->s_fwd.first;
+
+  // ---- backward alone (autograd path): dP comes from the caller
+  pl->s_bwd.first = int(pl->ph.size());
+  begin_phase(pl);
+  {
+    Args a = base_args(pl, 5);
+    int k = 0;
+    for (int l = 0; l < kNumHeavy; ++l) { a.zero_ptr[k] = u.stats_b[l]; a.zero_bytes[k] = 2 * kHidden * 8; ++k; }
+    if (add_ew(pl, EW_PREP, a)) return 1;
+    if (pl->large) {
+      Args z = base_args(pl, 5);
+      int q = 0;
+      for (int l = 0; l < kNumHeavy; ++l) { z.zero_ptr[q] = d.grads + kPL.b[l]; z.zero_bytes[q] = kHidden * 4; ++q; }
+      if (add_ew(pl, EW_PREP, z)) return 1;
+    }
+    Args s = base_args(pl, 5);
+    s.out_bm = u.dP_bm; s.out_fm = u.dP_fm; s.grad_bias = d.grads + kPL.b[5];
+    if (add_ew(pl, EW_SPLIT_DP, s)) return 1;
+  }
+  end_phase(pl);
+  if (build_backward(pl, false)) return 1;
+  pl->s_bwd.count = int(pl->ph.size()) - pl->s_bwd.first;
+
+  // ---- fused step (train_bilinear.py:75-83)
+  pl->s_step.first = int(pl->ph.size());
+  if (prep_fwd(true)) return 1;
+  for (int l = 0; l < kNumHeavy; ++l)
+    if (build_fwd_layer(pl, l, true)) return 1;
+  if (build_decode(pl, true)) return 1;
+  if (build_backward(pl, true)) return 1;
+  begin_phase(pl);
+  {
+    Args a = adam_args(pl);
+    a.src_cols = 1;  // bias / BN-affine gradients only: the weight tiles were summed in the wgrad epilogues
+    if (add_ew(pl, EW_SUMSQ, a)) return 1;
+  }
+  end_phase(pl);
+  begin_phase(pl);
+  if (add_ew(pl, EW_ADAM, adam_args(pl))) return 1;
+  end_phase(pl);
+  pl->s_step.count = int(pl->ph.size()) - pl->s_step.first;
+
+  // ---- optimizer alone (data parallel: after the gradient all-reduce; autograd path)
+  pl->s_update.first = int(pl->ph.size());
+  begin_phase(pl);
+  {
+    Args a = base_args(pl, 0);
+    a.zero_ptr[0] = u.gnorm2; a.zero_bytes[0] = 64;
+    if (add_ew(pl, EW_PREP, a)) return 1;
+  }
+  end_phase(pl);
+  begin_phase(pl);
+  {
+    Args a = adam_args(pl);
+    a.src_cols = 0;
+    if (add_ew(pl, EW_SUMSQ, a)) return 1;
+  }
+  end_phase(pl);
+  begin_phase(pl);
+  if (add_ew(pl, EW_ADAM, adam_args(pl))) return 1;
+  end_phase(pl);
+  pl->s_update.count = int(pl->ph.size()) - pl->s_update.first;
+  return 0;
+}
+
+static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, cudaStream_t stream) {
+  if (count <= 0) return fail("empty schedule (plan kind does not support this call)");
+  MegaParams p;
+  memset(&p, 0, sizeof p);
+  p.gemm_jobs = pl->u.gjobs;
+  p.ew_jobs = pl->u.ejobs;
+  p.phases = pl->u.phases + s.first;
+  p.tmaps = pl->u.tmaps;
+  p.barrier = pl->u.barrier;
+  p.num_phases = count;
+  p.dyn = dyn;
+  const bool coop = count > 1;
+  if (coop) CK(cudaMemsetAsync(pl->u.barrier, 0, 4, stream));
+  CK(launch_mega(p, pl->sms, coop, stream));
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+static Dyn make_dyn(const b200_train_args* t, const b200_adam_args* a) {
+  Dyn d;
+  memset(&d, 0, sizeof d);
+  for (int l = 0; l < kNumHeavy; ++l) d.momentum[l] = 0.1f;
+  d.grad_scale = 1.f;
+  d.bias_corr1 = 1.f; d.bias_corr2_sqrt = 1.f;
+  if (t) {
+    d.x = t->x; d.y = t->y; d.p_out = t->p_out; d.masks = t->masks;
+    d.seed = t->seed; d.step = t->step;
+    d.loss_out = t->loss_out; d.gnorm_out = t->gnorm_out;
+    for (int l = 0; l < kNumHeavy; ++l) d.momentum[l] = t->momentum[l];
+  }
+  if (a) {
+    d.lr = a->lr; d.beta1 = a->beta1; d.beta2 = a->beta2; d.adam_eps = a->eps;
+    // torch/optim/adam.py: bias_correction1 = 1 - beta1**step, bias_correction2_sqrt = sqrt(1 - beta2**step)
+    d.bias_corr1 = float(1.0 - std::pow(double(a->beta1), double(a->step)));
+    d.bias_corr2_sqrt = float(std::sqrt(1.0 - std::pow(double(a->beta2), double(a->step))));
+    d.max_norm = a->max_norm;
+    d.grad_scale = a->grad_scale;
+  }
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int b200_version(void) { return 100; }
+const char* b200_last_error(void) { return g_err.c_str(); }
+int64_t b200_param_numel(void) { return kPL.numel; }
+int64_t b200_launch_count(void) { return g_launches.load(); }
+
+int64_t b200_workspace_bytes(int32_t batch, int32_t precision, int32_t kind) {
+  if (batch < 1 || (precision != 1 && precision != 3)) return -1;
+  Carver c(nullptr);
+  Bufs u;
+  return carve(c, u, batch, precision, kind);
+}
+
+int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
+  if (!desc || !out) return fail("null argument");
+  if (desc->batch < 1) return fail("batch must be >= 1");
+  if (desc->precision != B200_PREC_BF16 && desc->precision != B200_PREC_FP32) return fail("bad precision");
+  if (desc->kind != B200_PLAN_TRAIN && desc->kind != B200_PLAN_INFER) return fail("bad plan kind");
+  if (!desc->params || !desc->workspace) return fail("params and workspace are required");
+  if (desc->kind == B200_PLAN_TRAIN && !desc->grads) return fail("training plan needs a gradient buffer");
+  if (reinterpret_cast<uintptr_t>(desc->workspace) % 1024) return fail("workspace must be 1024-byte aligned");
+  const int64_t need = b200_workspace_bytes(desc->batch, desc->precision, desc->kind);
+  if (desc->workspace_bytes < need)
+    return fail("workspace too small: %lld < %lld", (long long)desc->workspace_bytes, (long long)need);
+  for (int l = 0; l < kNumHeavy; ++l)
+    if (!desc->running_mean[l] || !desc->running_var[l]) return fail("BatchNorm buffers are required");
+  b200_plan* pl = new b200_plan();
+  pl->d = *desc;
+  pl->B = desc->batch; pl->P = desc->precision; pl->kind = desc->kind;
+  pl->large = pl->B > (pl->P == 1 ? 256 : 128);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  pl->sms = 148;
+  cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, dev);
+  Carver c(desc->workspace);
+  carve(c, pl->u, pl->B, pl->P, pl->kind);
+  if (build_plan(pl)) { delete pl; return 1; }
+  // schedules + tensor maps -> device (pageable host memory: cudaMemcpy is synchronous, done once)
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMemcpy(pl->u.tmaps, pl->tm.data(), pl->tm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->u.gjobs, pl->gj.data(), pl->gj.size() * sizeof(GemmJob), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->u.ejobs, pl->ej.data(), pl->ej.size() * sizeof(EwJob), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->u.phases, pl->ph.data(), pl->ph.size() * sizeof(Phase), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { delete pl; return fail("plan upload failed: %s", cudaGetErrorString(e)); }
+  *out = pl;
+  return 0;
+}
+
+void b200_plan_destroy(b200_plan* plan) { delete plan; }
+
+int b200_refresh_weights(b200_plan* plan, void* stream) {
+  if (!plan) return fail("null plan");
+  Dyn d = make_dyn(nullptr, nullptr);
+  return run_sched(plan, plan->s_refresh, plan->s_refresh.count, d, (cudaStream_t)stream);
+}
+
+int b200_forward_eval(b200_plan* plan, const float* x, float* p, void* stream) {
+  if (!plan || !x || !p) return fail("null argument");
+  Dyn d = make_dyn(nullptr, nullptr);
+  d.x = x; d.p_out = p;
+  return run_sched(plan, plan->s_eval, plan->s_eval.count, d, (cudaStream_t)stream);
+}
+
+int b200_forward_train(b200_plan* plan, const b200_train_args* args, void* stream) {
+  if (!plan || !args || !args->x) return fail("null argument");
+  if (plan->B < 2) return fail("Expected more than 1 value per channel when training, got input size [1, 1024]");
+  Dyn d = make_dyn(args, nullptr);
+  d.y = nullptr; d.loss_out = nullptr; d.gnorm_out = nullptr;
+  return run_sched(plan, plan->s_fwd, plan->s_fwd.count, d, (cudaStream_t)stream);
+}
+
+int b200_backward(b200_plan* plan, const float* dP, void* stream) {
+  if (!plan || !dP) return fail("null argument");
+  Dyn d = make_dyn(nullptr, nullptr);
+  d.dP = dP;
+  return run_sched(plan, plan->s_bwd, plan->s_bwd.count, d, (cudaStream_t)stream);
+}
+
+int b200_train_step(b200_plan* plan, const b200_train_args* targs, const b200_adam_args* aargs, int32_t update,
+                    void* stream) {
+  if (!plan || !targs || !targs->x || !targs->y) return fail("null argument");
+  if (update && (!aargs || !plan->d.exp_avg || !plan->d.exp_avg_sq)) return fail("optimizer state / args missing");
+  if (plan->B < 2) return fail("Expected more than 1 value per channel when training, got input size [1, 1024]");
+  Dyn d = make_dyn(targs, update ? aargs : nullptr);
+  // the mean loss is produced by the last phase that runs: Adam when updating, otherwise a tiny tail
+  int count = plan->s_step.count - (update ? 0 : 1);
+  int rc = run_sched(plan, plan->s_step, count, d, (cudaStream_t)stream);
+  if (rc) return rc;
+  return 0;
+}
+
+int b200_adam_step(b200_plan* plan, const b200_adam_args* aargs, float* gnorm_out, void* stream) {
+  if (!plan || !aargs) return fail("null argument");
+  if (!plan->d.exp_avg || !plan->d.exp_avg_sq) return fail("optimizer state missing");
+  Dyn d = make_dyn(nullptr, aargs);
+  d.gnorm_out = gnorm_out;
+  return run_sched(plan, plan->s_update, plan->s_update.count, d, (cudaStream_t)stream);
+}
+
+static int eval_common(const float* pred, const float* gt, const float* mean, const float* stddev, int64_t n,
+                       int32_t joints, const int32_t* action, int32_t n_actions, float* dist_out, float* pdist_out,
+                       double* acc_sum, double* pacc_sum, int64_t* acc_cnt, bool do_m, bool do_p, void* stream) {
+  if (!pred || !gt) return fail("null argument");
+  if (n < 0) return fail("negative pose count");
+  if (joints != 16 && joints != 17) return fail("joints must be 16 or 17");
+  if ((mean == nullptr) != (stddev == nullptr)) return fail("mean and stddev must be given together");
+  if (n_actions < 1 || n_actions > 64) return fail("n_actions must be in [1, 64]");
+  if (n == 0) return 0;
+  EvalParams prm;
+  prm.pred = pred; prm.gt = gt; prm.mean = mean; prm.stddev = stddev; prm.action = action;
+  prm.dist_out = dist_out; prm.pdist_out = pdist_out; prm.acc_sum = acc_sum; prm.pacc_sum = pacc_sum;
+  prm.acc_cnt = reinterpret_cast<long long*>(acc_cnt);
+  prm.n = n; prm.n_actions = n_actions;
+  CK(launch_eval(prm, joints, do_m, do_p, (cudaStream_t)stream));
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int b200_mpjpe(const float* pred, const float* gt, const float* mean, const float* stddev, int64_t n, int32_t joints,
+               const int32_t* action, int32_t n_actions, float* dist_out, double* acc_sum, int64_t* acc_cnt,
+               void* stream) {
+  return eval_common(pred, gt, mean, stddev, n, joints, action, n_actions, dist_out, nullptr, acc_sum, nullptr, acc_cnt,
+                     true, false, stream);
+}
+int b200_pmpjpe(const float* pred, const float* gt, const float* mean, const float* stddev, int64_t n, int32_t joints,
+                const int32_t* action, int32_t n_actions, float* dist_out, double* acc_sum, int64_t* acc_cnt,
+                void* stream) {
+  return eval_common(pred, gt, mean, stddev, n, joints, action, n_actions, nullptr, dist_out, nullptr, acc_sum, acc_cnt,
+                     false, true, stream);
+}
+int b200_mpjpe_pmpjpe(const float* pred, const float* gt, const float* mean, const float* stddev, int64_t n,
+                      int32_t joints, const int32_t* action, int32_t n_actions, float* dist_out, float* pdist_out,
+                      double* acc_sum, double* pacc_sum, int64_t* acc_cnt, void* stream) {
+  return eval_common(pred, gt, mean, stddev, n, joints, action, n_actions, dist_out, pdist_out, acc_sum, pacc_sum,
+                     acc_cnt, true, true, stream);
+}
+
+// ---- debug GEMM: one single-phase schedule built on the fly in `scratch` (>= 64 KiB)
+int b200_debug_gemm(const uint16_t* a, const uint16_t* b, float* dmat, int32_t m, int32_t n, int32_t k, int32_t planes,
+                    int32_t a_mn, int32_t b_mn, int32_t bn, void* scratch, int64_t scratch_bytes, void* stream) {
+  if (!a || !b || !dmat || !scratch) return fail("null argument");
+  if (scratch_bytes < 65536 || reinterpret_cast<uintptr_t>(scratch) % 1024) return fail("scratch: 64 KiB, 1 KiB aligned");
+  if (bn % 16 || bn < 16 || bn > 256 || (b_mn && bn % 64)) return fail("bad bn");
+  if (planes != 1 && planes != 3) return fail("bad planes");
+  uint8_t* s = reinterpret_cast<uint8_t*>(scratch);
+  CUtensorMap tm[2];
+  if (!a_mn) { if (encode_map(&tm[0], a, k, m, planes, k, int64_t(m) * k, 128)) return 1; }
+  else       { if (encode_map(&tm[0], a, m, k, planes, m, int64_t(m) * k, 64)) return 1; }
+  if (!b_mn) { if (encode_map(&tm[1], b, k, n, planes, k, int64_t(n) * k, bn)) return 1; }
+  else       { if (encode_map(&tm[1], b, n, k, planes, n, int64_t(n) * k, 64)) return 1; }
+  GemmJob g;
+  memset(&g, 0, sizeof g);
+  g.tmap_a = 0; g.tmap_b = 1; g.a_mn = a_mn; g.b_mn = b_mn;
+  g.M = m; g.N = n; g.K = k; g.BN = bn;
+  g.m_tiles = (m + 127) / 128; g.n_tiles = (n + bn - 1) / bn; g.num_tiles = g.m_tiles * g.n_tiles;
+  g.epi = EPI_STORE_F32;
+  g.a.planes = planes; g.a.out_f32 = dmat; g.a.ld_out = n;
+  Phase ph;
+  memset(&ph, 0, sizeof ph);
+  ph.first_gemm = 0; ph.num_gemm = 1; ph.gemm_tiles = g.num_tiles;
+  ph.stage_bytes = planes * (128 * 128 + bn * 128);
+  ph.num_stages = std::max(1, std::min(8, mega_ring_bytes() / ph.stage_bytes));
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(s, tm, sizeof tm, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s + 1024, &g, sizeof g, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s + 1024 + 4096, &ph, sizeof ph, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // the host staging copies above live on this stack frame
+  MegaParams p;
+  memset(&p, 0, sizeof p);
+  p.tmaps = s; p.gemm_jobs = reinterpret_cast<GemmJob*>(s + 1024); p.phases = reinterpret_cast<Phase*>(s + 1024 + 4096);
+  p.ew_jobs = nullptr; p.barrier = reinterpret_cast<unsigned int*>(s + 1024 + 8192); p.num_phases = 1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CK(launch_mega(p, std::min(sms, g.num_tiles), false, st));
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+__global__ void split_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t numel, int planes) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < numel; i += int64_t(gridDim.x) * blockDim.x) {
+    float v = src[i];
+    for (int p = 0; p < planes; ++p) {
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      dst[int64_t(p) * numel + i] = __bfloat16_as_ushort(h);
+      v -= __bfloat162float(h);
+    }
+  }
+}
+int b200_debug_split(const float* src, uint16_t* dst, int64_t numel, int32_t planes, void* stream) {
+  if (!src || !dst) return fail("null argument");
+  const int grid = int(std::min<int64_t>(4096, (numel + 255) / 256));
+  split_kernel<<<std::max(grid, 1), 256, 0, (cudaStream_t)stream>>>(src, dst, numel, planes);
+  CK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+}  // extern "C"

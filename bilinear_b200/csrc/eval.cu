@@ -1,0 +1,353 @@
+// H36M evaluation math on sm_100a: MPJPE (reference valid_bilinear.py:53-60, per-action fp64
+// accumulation of :61-70) and Procrustes-aligned P-MPJPE (not in the reference; SURVEY.md
+// Appendix B gives the specification the oracle follows).
+//
+// Both are HBM-bound: 2 * J * 3 * 4 bytes are read per pose (384 B at J = 16) and at most 8 bytes
+// written.  Layout of the work:
+//   - a persistent grid (4 CTAs per SM) walks chunks of 128 poses;
+//   - the 128 threads of a CTA stream the chunk with 128-bit coalesced loads (24 float4 in flight per
+//     thread) into shared memory with an odd row pitch (3J+1 words -> conflict-free per-pose reads);
+//   - then ONE THREAD PER POSE pulls its 2*3J values into registers and does the whole per-pose
+//     computation there (no cross-lane traffic): centroids, 3x3 correlation, optimal rotation via
+//     Horn's quaternion form -- largest eigenvalue of the 4x4 key matrix by Newton iteration on its
+//     characteristic quartic (the QCP method), eigenvector from the adjugate -- scale, aligned
+//     distances.  Degenerate poses (repeated top eigenvalue, zero extent) fall back to a cyclic
+//     Jacobi eigen-solver / the unaligned distance, so the result is always finite.
+//   - per-action sums are accumulated in fp64 in shared memory and flushed once per CTA.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int kEvalThreads = 128;
+constexpr int kMaxActions = 64;
+
+struct EvalParams {
+  const float* pred;
+  const float* gt;
+  const float* mean;    // [3J] or nullptr
+  const float* stddev;  // [3J] or nullptr
+  const int32_t* action;
+  float* dist_out;
+  float* pdist_out;
+  double* acc_sum;
+  double* pacc_sum;
+  long long* acc_cnt;
+  int64_t n;
+  int32_t n_actions;
+};
+
+// ---- 4x4 symmetric eigen fallback (cyclic Jacobi), only for degenerate poses ------------------
+__device__ __noinline__ void jacobi4_top(const float* Nm, float& lam, float* q) {
+  float A[4][4], V[4][4];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) { A[i][j] = Nm[i * 4 + j]; V[i][j] = (i == j) ? 1.f : 0.f; }
+  for (int sweep = 0; sweep < 8; ++sweep) {
+    for (int p = 0; p < 3; ++p)
+      for (int r = p + 1; r < 4; ++r) {
+        const float apq = A[p][r];
+        if (fabsf(apq) < 1e-20f) continue;
+        const float theta = (A[r][r] - A[p][p]) / (2.f * apq);
+        const float t = copysignf(1.f, theta) / (fabsf(theta) + sqrtf(theta * theta + 1.f));
+        const float c = rsqrtf(t * t + 1.f), s = t * c;
+        for (int k = 0; k < 4; ++k) {
+          const float akp = A[k][p], akq = A[k][r];
+          A[k][p] = c * akp - s * akq;
+          A[k][r] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 4; ++k) {
+          const float apk = A[p][k], aqk = A[r][k];
+          A[p][k] = c * apk - s * aqk;
+          A[r][k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 4; ++k) {
+          const float vkp = V[k][p], vkq = V[k][r];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][r] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int best = 0;
+  for (int i = 1; i < 4; ++i)
+    if (A[i][i] > A[best][best]) best = i;
+  lam = A[best][best];
+  for (int k = 0; k < 4; ++k) q[k] = V[k][best];
+}
+
+__device__ __forceinline__ float det3(float a, float b, float c, float d, float e, float f, float g, float h, float i) {
+  return a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+}
+
+// Largest eigenvalue / eigenvector of Horn's key matrix for the normalised correlation S (3x3,
+// S[a][b] = sum_j p_a g_b with |P0|_F = |G0|_F = 1).  Returns lambda_max = s1 + s2 + sign(det) s3.
+__device__ __forceinline__ void horn_top(const float S[3][3], float& lam, float q[4]) {
+  const float Sxx = S[0][0], Sxy = S[0][1], Sxz = S[0][2];
+  const float Syx = S[1][0], Syy = S[1][1], Syz = S[1][2];
+  const float Szx = S[2][0], Szy = S[2][1], Szz = S[2][2];
+  float Nm[16];
+  Nm[0] = Sxx + Syy + Szz; Nm[1] = Syz - Szy;        Nm[2] = Szx - Sxz;         Nm[3] = Sxy - Syx;
+  Nm[4] = Nm[1];           Nm[5] = Sxx - Syy - Szz;  Nm[6] = Sxy + Syx;         Nm[7] = Szx + Sxz;
+  Nm[8] = Nm[2];           Nm[9] = Nm[6];            Nm[10] = -Sxx + Syy - Szz; Nm[11] = Syz + Szy;
+  Nm[12] = Nm[3];          Nm[13] = Nm[7];           Nm[14] = Nm[11];           Nm[15] = -Sxx - Syy + Szz;
+
+  // characteristic polynomial l^4 + c2 l^2 + c1 l + c0 (the key matrix is traceless)
+  const float c2 = -2.f * (Sxx * Sxx + Sxy * Sxy + Sxz * Sxz + Syx * Syx + Syy * Syy + Syz * Syz + Szx * Szx +
+                           Szy * Szy + Szz * Szz);
+  const float c1 = -8.f * det3(Sxx, Sxy, Sxz, Syx, Syy, Syz, Szx, Szy, Szz);
+  const float a = Nm[0], b = Nm[1], c = Nm[2], d = Nm[3], e = Nm[5], f = Nm[6], g = Nm[7], h = Nm[10], i = Nm[11],
+              j = Nm[15];
+  // det of the symmetric 4x4 [[a b c d][b e f g][c f h i][d g i j]] by 2x2 minors of rows (0,1)x(2,3)
+  const float s0 = a * e - b * b, s1 = a * f - b * c, s2 = a * g - b * d, s3 = b * f - e * c, s4 = b * g - e * d,
+              s5 = c * g - f * d;
+  const float t5 = h * j - i * i, t4 = f * j - i * g, t3 = f * i - h * g, t2 = c * j - i * d, t1 = c * i - h * d,
+              t0 = c * g - f * d;
+  const float c0 = s0 * t5 - s1 * t4 + s2 * t3 + s3 * t2 - s4 * t1 + s5 * t0;
+
+  // Newton from the upper bound (|P0|^2 + |G0|^2)/2 = 1: monotone convergence to the top root
+  float l = 1.0f;
+#pragma unroll 1
+  for (int it = 0; it < 24; ++it) {
+    const float l2 = l * l;
+    const float pv = (l2 + c2) * l2 + c1 * l + c0;
+    const float dv = (4.f * l2 + 2.f * c2) * l + c1;
+    if (!(fabsf(dv) > 1e-30f)) break;
+    const float step = pv / dv;
+    l -= step;
+    if (fabsf(step) < 1e-7f * fabsf(l)) break;
+  }
+  lam = l;
+
+  // eigenvector: a column of adj(N - lam I) (= const * q q^T when the top eigenvalue is simple)
+  const float m00 = Nm[0] - l, m11 = Nm[5] - l, m22 = Nm[10] - l, m33 = Nm[15] - l;
+  const float m01 = Nm[1], m02 = Nm[2], m03 = Nm[3], m12 = Nm[6], m13 = Nm[7], m23 = Nm[11];
+  // diagonal cofactors
+  const float C00 = det3(m11, m12, m13, m12, m22, m23, m13, m23, m33);
+  const float C11 = det3(m00, m02, m03, m02, m22, m23, m03, m23, m33);
+  const float C22 = det3(m00, m01, m03, m01, m11, m13, m03, m13, m33);
+  const float C33 = det3(m00, m01, m02, m01, m11, m12, m02, m12, m22);
+  // off-diagonal cofactors C_ij = (-1)^(i+j) det(minor_ij)
+  const float C01 = -det3(m01, m12, m13, m02, m22, m23, m03, m23, m33);
+  const float C02 = det3(m01, m11, m13, m02, m12, m23, m03, m13, m33);
+  const float C03 = -det3(m01, m11, m12, m02, m12, m22, m03, m13, m23);
+  const float C12 = -det3(m00, m01, m03, m02, m12, m23, m03, m13, m33);
+  const float C13 = det3(m00, m01, m02, m02, m12, m22, m03, m13, m23);
+  const float C23 = -det3(m00, m01, m02, m01, m11, m12, m03, m13, m23);
+  const float a0 = fabsf(C00), a1 = fabsf(C11), a2 = fabsf(C22), a3 = fabsf(C33);
+  float q0, q1, q2, q3;
+  if (a0 >= a1 && a0 >= a2 && a0 >= a3) { q0 = C00; q1 = C01; q2 = C02; q3 = C03; }
+  else if (a1 >= a2 && a1 >= a3) { q0 = C01; q1 = C11; q2 = C12; q3 = C13; }
+  else if (a2 >= a3) { q0 = C02; q1 = C12; q2 = C22; q3 = C23; }
+  else { q0 = C03; q1 = C13; q2 = C23; q3 = C33; }
+  const float nn = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
+  if (nn > 1e-16f) {
+    const float r = rsqrtf(nn);
+    q[0] = q0 * r; q[1] = q1 * r; q[2] = q2 * r; q[3] = q3 * r;
+  } else {
+    jacobi4_top(Nm, lam, q);  // repeated top eigenvalue (collinear / reflected-degenerate pose)
+    const float r = rsqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    q[0] *= r; q[1] *= r; q[2] *= r; q[3] *= r;
+  }
+}
+
+template <int J, bool DO_M, bool DO_P>
+__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams prm) {
+  constexpr int W = 3 * J;          // floats per pose
+  constexpr int PITCH = W | 1;      // odd pitch: per-pose rows hit distinct banks
+  constexpr int CH = kEvalThreads;  // poses per chunk
+  extern __shared__ float sm[];
+  float* sP = sm;
+  float* sG = sm + CH * PITCH;
+  float* sMean = sG + CH * PITCH;
+  float* sStd = sMean + W;
+  __shared__ double accS[kMaxActions], accPS[kMaxActions];
+  __shared__ unsigned long long accC[kMaxActions];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kMaxActions; i += CH) { accS[i] = 0.0; accPS[i] = 0.0; accC[i] = 0ull; }
+  const bool unnorm = prm.mean != nullptr;
+  for (int i = tid; i < W; i += CH) {
+    sMean[i] = unnorm ? prm.mean[i] : 0.f;
+    sStd[i] = unnorm ? prm.stddev[i] : 1.f;
+  }
+  __syncthreads();
+
+  const int64_t nchunks = (prm.n + CH - 1) / CH;
+  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int64_t p0 = ch * CH;
+    const int np = int(min(int64_t(CH), prm.n - p0));
+    const int nfl = np * W;                       // floats in this chunk (per tensor)
+    const float* gp = prm.pred + p0 * W;
+    const float* gg = prm.gt + p0 * W;
+    // chunk base is 16-byte aligned: p0 * W * 4 = ch * 128 * W * 4
+    constexpr int V4 = CH * W / 4;                // float4 per tensor per full chunk
+    constexpr int PER = (V4 + CH - 1) / CH;
+    float4 rp[PER], rg[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int v = tid + k * CH;
+      if (4 * v + 3 < nfl) {
+        rp[k] = __ldcs(reinterpret_cast<const float4*>(gp) + v);
+        rg[k] = __ldcs(reinterpret_cast<const float4*>(gg) + v);
+      } else {
+        float tp[4], tg[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int idx = 4 * v + e;
+          tp[e] = (idx < nfl) ? gp[idx] : 0.f;
+          tg[e] = (idx < nfl) ? gg[idx] : 0.f;
+        }
+        rp[k] = make_float4(tp[0], tp[1], tp[2], tp[3]);
+        rg[k] = make_float4(tg[0], tg[1], tg[2], tg[3]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int v = tid + k * CH;
+      if (v < V4) {
+        const float tp[4] = {rp[k].x, rp[k].y, rp[k].z, rp[k].w};
+        const float tg[4] = {rg[k].x, rg[k].y, rg[k].z, rg[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int idx = 4 * v + e;
+          const int pose = idx / W, w = idx - pose * W;
+          sP[pose * PITCH + w] = tp[e];
+          sG[pose * PITCH + w] = tg[e];
+        }
+      }
+    }
+    __syncthreads();
+
+    if (tid < np) {
+      float P[W], G[W];
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        P[w] = sStd[w] * sP[tid * PITCH + w] + sMean[w];   // valid_bilinear.py:53
+        G[w] = sStd[w] * sG[tid * PITCH + w] + sMean[w];   // valid_bilinear.py:54
+      }
+      float dist = 0.f, pdist = 0.f;
+      if (DO_M) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const float dx = P[3 * j] - G[3 * j], dy = P[3 * j + 1] - G[3 * j + 1], dz = P[3 * j + 2] - G[3 * j + 2];
+          dist += sqrtf(dx * dx + dy * dy + dz * dz);        // valid_bilinear.py:60
+        }
+      }
+      if (DO_P) {
+        float mp[3] = {0.f, 0.f, 0.f}, mg[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+#pragma unroll
+          for (int a = 0; a < 3; ++a) { mp[a] += P[3 * j + a]; mg[a] += G[3 * j + a]; }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { mp[a] *= (1.f / J); mg[a] *= (1.f / J); }
+        float nP2 = 0.f, nG2 = 0.f;
+        float S[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          float pc[3], gc[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            pc[a] = P[3 * j + a] - mp[a];
+            gc[a] = G[3 * j + a] - mg[a];
+            P[3 * j + a] = pc[a];
+            G[3 * j + a] = gc[a];
+            nP2 += pc[a] * pc[a];
+            nG2 += gc[a] * gc[a];
+          }
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) S[a][b] += pc[a] * gc[b];
+        }
+        if (nP2 > 0.f && nG2 > 0.f) {
+          const float inv = rsqrtf(nP2) * rsqrtf(nG2);
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) S[a][b] *= inv;
+          float lam, q[4];
+          horn_top(S, lam, q);
+          const float scale = lam * sqrtf(nG2) * rsqrtf(nP2);   // tr * nG / nP (Appendix B)
+          const float q0 = q[0], qx = q[1], qy = q[2], qz = q[3];
+          const float R00 = q0 * q0 + qx * qx - qy * qy - qz * qz, R01 = 2.f * (qx * qy - q0 * qz),
+                      R02 = 2.f * (qx * qz + q0 * qy);
+          const float R10 = 2.f * (qy * qx + q0 * qz), R11 = q0 * q0 - qx * qx + qy * qy - qz * qz,
+                      R12 = 2.f * (qy * qz - q0 * qx);
+          const float R20 = 2.f * (qz * qx - q0 * qy), R21 = 2.f * (qz * qy + q0 * qx),
+                      R22 = q0 * q0 - qx * qx - qy * qy + qz * qz;
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            const float px = P[3 * j], py = P[3 * j + 1], pz = P[3 * j + 2];
+            const float ax = scale * (R00 * px + R01 * py + R02 * pz) - G[3 * j];
+            const float ay = scale * (R10 * px + R11 * py + R12 * pz) - G[3 * j + 1];
+            const float az = scale * (R20 * px + R21 * py + R22 * pz) - G[3 * j + 2];
+            pdist += sqrtf(ax * ax + ay * ay + az * az);
+          }
+        } else {
+          // zero-extent pose: alignment undefined -> unaligned distance of the (uncentred) poses
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            const float dx = (P[3 * j] + mp[0]) - (G[3 * j] + mg[0]);
+            const float dy = (P[3 * j + 1] + mp[1]) - (G[3 * j + 1] + mg[1]);
+            const float dz = (P[3 * j + 2] + mp[2]) - (G[3 * j + 2] + mg[2]);
+            pdist += sqrtf(dx * dx + dy * dy + dz * dz);
+          }
+        }
+      }
+      const int64_t gi = p0 + tid;
+      if (DO_M && prm.dist_out) prm.dist_out[gi] = dist;
+      if (DO_P && prm.pdist_out) prm.pdist_out[gi] = pdist;
+      int act = prm.action ? prm.action[gi] : 0;
+      act = min(max(act, 0), prm.n_actions - 1);
+      if (DO_M) atomicAdd(&accS[act], double(dist));      // valid_bilinear.py:68 (np.double accumulation)
+      if (DO_P) atomicAdd(&accPS[act], double(pdist));
+      atomicAdd(&accC[act], 1ull);
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < prm.n_actions; i += CH) {
+    if (accC[i] != 0ull) {
+      if (DO_M && prm.acc_sum) atomicAdd(prm.acc_sum + i, accS[i]);
+      if (DO_P && prm.pacc_sum) atomicAdd(prm.pacc_sum + i, accPS[i]);
+      if (prm.acc_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(prm.acc_cnt) + i, accC[i]);
+    }
+  }
+}
+
+template <int J, bool DO_M, bool DO_P>
+static cudaError_t launch_eval_t(const EvalParams& prm, cudaStream_t stream) {
+  constexpr int W = 3 * J, PITCH = W | 1;
+  const size_t smem = size_t(2 * kEvalThreads * PITCH + 2 * W) * sizeof(float);
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(eval_kernel<J, DO_M, DO_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t nchunks = (prm.n + kEvalThreads - 1) / kEvalThreads;
+  const int grid = int(std::max<int64_t>(1, std::min<int64_t>(nchunks, int64_t(sms) * 4)));
+  eval_kernel<J, DO_M, DO_P><<<grid, kEvalThreads, smem, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_eval(const EvalParams& prm, int joints, bool do_m, bool do_p, cudaStream_t stream) {
+  if (joints == 16) {
+    if (do_m && do_p) return launch_eval_t<16, true, true>(prm, stream);
+    if (do_m) return launch_eval_t<16, true, false>(prm, stream);
+    return launch_eval_t<16, false, true>(prm, stream);
+  }
+  if (joints == 17) {
+    if (do_m && do_p) return launch_eval_t<17, true, true>(prm, stream);
+    if (do_m) return launch_eval_t<17, true, false>(prm, stream);
+    return launch_eval_t<17, false, true>(prm, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace b200

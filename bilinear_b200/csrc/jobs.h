@@ -1,0 +1,174 @@
+// Schedule description shared by host (plan builder, api.cu) and device (mega.cu).
+//
+// The whole pose-lifting hot path (reference: model/bilinear.py:7-41 forward, autograd backward
+// driven by train_bilinear.py:75-83, clip + Adam) is expressed as a list of PHASES executed by one
+// persistent kernel; a phase is a set of GEMM tile jobs and/or elementwise jobs that have no
+// dependencies among themselves, and consecutive phases are separated by a grid-wide barrier.
+// Launching a single-phase schedule gives a per-layer kernel; launching the full list gives the
+// persistent whole-network kernel (cooperative launch).
+//
+// Geometry convention for every GEMM job: D[m][n] = sum_k A[m][k] * B[n][k]
+//   m  (TMEM lane / one epilogue thread per row) = an output FEATURE,
+//   n  (TMEM column)                              = a BATCH index (fwd/dgrad) or an input feature (wgrad).
+// With features on the lanes, every BatchNorm reduction (forward mean/var, backward sum(dy),
+// sum(dy*xhat)) is a per-thread loop over TMEM columns instead of a cross-thread reduction.
+#pragma once
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kHidden = 1024;
+constexpr int kDin = 32;    // 2 * 16 joints (reference model/bilinear.py:20-22)
+constexpr int kDout = 48;   // 3 * 16 joints (reference model/bilinear.py:29)
+constexpr int kNumLinear = 6;
+constexpr int kNumHeavy = 5;
+constexpr float kBnEps = 1e-5f;  // nn.BatchNorm1d default
+
+enum EpiKind : int32_t {
+  EPI_STORE_F32 = 0,   // D -> out_f32[m][n]                       (debug / unit test)
+  EPI_FWD_SMALL = 1,   // whole batch in one tile: bias+BN(batch stats)+ReLU+dropout(+skip)
+  EPI_FWD_LARGE = 2,   // bias, write z, per-tile partial sum / sumsq -> stats
+  EPI_FWD_EVAL = 3,    // scale*acc+shift, ReLU (+skip)            (BN folded, eval mode)
+  EPI_DECODE = 4,      // bias -> p[b][48]; optional fused MSE loss + dP
+  EPI_DGRAD_SMALL = 5, // da (+skip grad) -> full BN backward in-tile -> dz
+  EPI_DGRAD_LARGE = 6, // da (+skip grad) -> dy, partial sum(dy), sum(dy*xhat) -> stats
+  EPI_WGRAD = 7,       // dW tile -> flat grad buffer + sum of squares
+};
+
+enum EwKind : int32_t {
+  EW_PREP = 0,         // zero accumulators, split x into planes (+transposed), bump BN counters
+  EW_DROPBITS = 1,     // pack injected uint8 masks / generate Philox bits -> [f][b/32] words
+  EW_BN_FOLD = 2,      // eval: scale = g*rsqrt(rv+eps), shift = b + (bias-rm)*scale
+  EW_BN_FWD_APPLY = 3, // large path: z -> h (both layouts) + keep bits + running stats
+  EW_BN_BWD_APPLY = 4, // large path: dy,z -> dz (both layouts) + db
+  EW_SPLIT_DP = 5,     // external dP [B][48] fp32 -> planes (both layouts) + db5 (autograd path)
+  EW_SUMSQ = 6,        // sum of squares of the flat gradient (data-parallel path, after allreduce)
+  EW_ADAM = 7,         // clip coefficient + Adam + refresh bf16 operand planes of the weights
+  EW_SPLIT_W = 8,      // fp32 master weights -> bf16 operand planes (both layouts), no update
+};
+
+// bf16 "plane" tensor: value = sum_p plane[p].  planes = 1 (bf16 mode) or 3 (fp32-parity mode:
+// 3 x 8 significand bits carry a full fp32 value; the GEMM issues the 6 significant cross products).
+struct PlaneRef {
+  uint16_t* p;           // bf16 bits
+  int64_t plane_stride;  // elements between planes
+  int64_t ld;            // elements between rows
+};
+
+// Per-call values.  Schedules (jobs, tensor maps) are built once per plan and live in device memory;
+// everything that changes from one call to the next travels in the kernel parameters instead.
+struct Dyn {
+  const float* x;          // [B][32] fp32 network input           (train_bilinear.py:62,72)
+  const float* y;          // [B][48] fp32 regression target       (train_bilinear.py:63,73)
+  float* p_out;            // [B][48] fp32 prediction (nullptr: not stored)
+  const float* dP;         // [B][48] fp32 upstream gradient (autograd path)
+  const uint8_t* masks;    // [5][B][1024] injected dropout keep masks (nullptr: Philox)
+  float* loss_out;         // mean MSE of this step
+  float* gnorm_out;        // pre-clip global gradient norm
+  uint64_t seed, step;     // Philox key / counter salt
+  float lr, beta1, beta2, adam_eps, bias_corr1, bias_corr2_sqrt;
+  float max_norm;          // clip_grad_norm_ max_norm (<= 0: no clipping)
+  float grad_scale;        // 1 / world_size under data parallel
+  float momentum[kNumHeavy];  // >= 0: BN momentum; < 0: cumulative average (momentum=None)
+};
+
+enum DynSrc : int32_t { SRC_NONE = 0, SRC_X = 1, SRC_DP = 2 };
+
+constexpr int kMaxZero = 8;
+
+struct Args {
+  // ---- generic
+  int32_t layer;           // 0..5
+  int32_t planes;          // 1 | 3
+  int32_t B;               // batch rows in this launch
+  int32_t fuse_loss;       // decode: 1 = fused MSE loss + dP
+  // ---- fp32 outputs / inputs
+  float* out_f32;          // STORE: D; DECODE: p[b][48]; WGRAD: dW [out][in]
+  int64_t ld_out;
+  const float* bias;       // Linear bias [M]
+  const float* gamma;      // BN weight  [M]
+  const float* beta;       // BN bias    [M]
+  float* run_mean;         // BN running_mean [M]   (updated in train)
+  float* run_var;          // BN running_var  [M]
+  const int64_t* nbt;      // BN num_batches_tracked (already incremented by EW_PREP)
+  float* save_mean;        // [M] batch mean saved for backward
+  float* save_rstd;        // [M] batch 1/sqrt(var+eps)
+  double* stats;           // [M][2] accumulators (large path fwd: sum z, sum z^2; bwd: sum dy, sum dy*xhat)
+  const float* scale;      // eval: folded BN scale [M]
+  const float* shift;      // eval: folded BN shift [M]
+  float* scale_w;          // EW_BN_FOLD outputs
+  float* shift_w;
+  // ---- feature-major scratch ([f][ldT])
+  void* zT;                // pre-BN activations, fp32 (planes==3) or bf16 (planes==1)
+  void* dyT;               // large path: masked upstream grad, same dtype rule as zT
+  int64_t ldT;             // row stride (elements) of zT / dyT / G*
+  uint32_t* keep;          // [f][ldw] bit j of word w <-> b = 32 w + j : dropout_keep & (y > 0)
+  const uint32_t* drop;    // [f][ldw] dropout keep bits (nullptr => all ones)
+  int64_t ldw;
+  const float* skip_in;    // dgrad: gradient arriving over the residual edge  [f][ldT] (nullptr: none)
+  float* g_out;            // dgrad: total gradient at this layer's output, kept for a later skip
+  PlaneRef skip_fm;        // fwd: residual input, feature-major planes (p == nullptr: none)
+  // ---- plane outputs
+  PlaneRef out_bm;         // batch-major   [b][f]
+  PlaneRef out_fm;         // feature-major [f][b]
+  // ---- decode / loss
+  double* loss_acc;        // sum (p-y)^2
+  float* grad_bias;        // db   (decode: [48]; heavy: [M])
+  float* grad_gamma;       // dgamma [M]
+  float* grad_beta;        // dbeta  [M]
+  double* gnorm2;          // sum g^2 accumulator
+  // ---- elementwise extras
+  int32_t src;             // DynSrc: which per-call tensor EW_PREP / EW_SPLIT_DP splits into planes
+  int32_t src_cols;        // EW_PREP: columns of the source; EW_SUMSQ: 1 = non-weight tensors only
+  void* zero_ptr[kMaxZero];     // EW_PREP: regions to clear (16-byte multiples)
+  int64_t zero_bytes[kMaxZero];
+  int64_t* nbt_w[kNumHeavy];    // EW_PREP: BN counters to increment (nullptr: skip)
+  // ---- Adam
+  float* params;           // flat fp32 master parameters (reference parameters() order)
+  float* grads;            // flat fp32 gradients
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+  int64_t w_off[kNumLinear];   // offsets of the six Linear weights in the flat buffer
+  int32_t w_rows[kNumLinear];
+  int32_t w_cols[kNumLinear];
+  PlaneRef w_planes[kNumLinear];   // [out][in]
+  PlaneRef wT_planes[kNumLinear];  // [in][out]  (p == nullptr: not maintained)
+};
+
+struct GemmJob {
+  int32_t tmap_a, tmap_b;  // indices into the tensor-map table
+  int32_t a_mn, b_mn;      // 1: operand is MN-major in shared memory (global layout [k][mn])
+  int32_t M, N, K;
+  int32_t BN;              // tile width == UMMA N (multiple of 16, <= 256)
+  int32_t m_tiles, n_tiles, num_tiles;
+  int32_t epi;
+  Args a;
+};
+
+struct EwJob {
+  int32_t kind;
+  int32_t pad;
+  Args a;
+};
+
+struct Phase {
+  int32_t first_gemm, num_gemm, gemm_tiles;
+  int32_t first_ew, num_ew;
+  int32_t stage_bytes;      // smem ring geometry of this phase (max over its GEMM jobs)
+  int32_t num_stages;
+  int32_t pad;
+};
+
+struct MegaParams {
+  const GemmJob* gemm_jobs;
+  const EwJob* ew_jobs;
+  const Phase* phases;
+  const void* tmaps;        // array of CUtensorMap (128 B each, 64 B aligned)
+  unsigned int* barrier;    // grid barrier counter (zeroed before launch)
+  int32_t num_phases;
+  int32_t pad;
+  Dyn dyn;
+};
+
+}  // namespace b200
