@@ -747,7 +747,7 @@ int b200_debug_gemm(const uint16_t* a, const uint16_t* b, float* dmat, int32_t m
                     int32_t a_mn, int32_t b_mn, int32_t bn, void* scratch, int64_t scratch_bytes, void* stream) {
   if (!a || !b || !dmat || !scratch) return fail("null argument");
   if (scratch_bytes < 65536 || reinterpret_cast<uintptr_t>(scratch) % 1024) return fail("scratch: 64 KiB, 1 KiB aligned");
-  if (bn % 16 || bn < 16 || bn > 256 || (b_mn && bn % 64)) return fail("bad bn");
+  if (bn % 16 || bn < 16 || bn > 256 || (b_mn && bn % 64) || (planes == 3 && bn > 128)) return fail("bad bn");
   if (planes != 1 && planes != 3) return fail("bad planes");
   uint8_t* s = reinterpret_cast<uint8_t*>(scratch);
   CUtensorMap tm[2];

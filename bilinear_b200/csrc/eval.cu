@@ -243,6 +243,9 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams prm
           for (int a = 0; a < 3; ++a) { mp[a] += P[3 * j + a]; mg[a] += G[3 * j + a]; }
 #pragma unroll
         for (int a = 0; a < 3; ++a) { mp[a] *= (1.f / J); mg[a] *= (1.f / J); }
+        float rawP2 = 0.f, rawG2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < W; ++w) { rawP2 += P[w] * P[w]; rawG2 += G[w] * G[w]; }
         float nP2 = 0.f, nG2 = 0.f;
         float S[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
 #pragma unroll
@@ -262,7 +265,8 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams prm
 #pragma unroll
             for (int b = 0; b < 3; ++b) S[a][b] += pc[a] * gc[b];
         }
-        if (nP2 > 0.f && nG2 > 0.f) {
+        // zero-extent convention shared with oracle/pose_metrics.py (DEGENERATE_REL)
+        if (nP2 > 1e-10f * rawP2 && nG2 > 1e-10f * rawG2) {
           const float inv = rsqrtf(nP2) * rsqrtf(nG2);
 #pragma unroll
           for (int a = 0; a < 3; ++a)

@@ -32,6 +32,8 @@ def mpjpe_per_pose(pred, gt, mean=None, std=None):
     p = unnormalise(pred, mean, std)
     g = unnormalise(gt, mean, std)
     n = p.shape[0]
+    if n == 0:
+        return np.zeros(0, dtype=np.float64)
     p = p.reshape(n, -1, 3)
     g = g.reshape(n, -1, 3)
     return np.sqrt(((p - g) ** 2).sum(axis=2)).sum(axis=1)
@@ -49,6 +51,9 @@ def per_action_report(dist, action, n_actions, joints):
     return total, count, per_action, avg
 
 
+DEGENERATE_REL = 1e-10
+
+
 def procrustes_align(P, G):
     """SURVEY.md Appendix B for one pose.  P, G: [J, 3] float64.  Returns the aligned prediction."""
     muG = G.mean(axis=0)
@@ -57,8 +62,11 @@ def procrustes_align(P, G):
     P0 = P - muP
     nG = np.sqrt((G0 ** 2).sum())
     nP = np.sqrt((P0 ** 2).sum())
-    if nG == 0.0 or nP == 0.0:
-        return P.copy()  # convention: alignment undefined -> unaligned pose
+    # convention (stated, since nothing in the reference defines it): a pose whose extent about its
+    # centroid is below 1e-5 of its raw magnitude (extent^2 <= DEGENERATE_REL * sum |x|^2) has no
+    # orientation -> alignment undefined -> the UNALIGNED prediction is measured
+    if nG ** 2 <= DEGENERATE_REL * (G ** 2).sum() or nP ** 2 <= DEGENERATE_REL * (P ** 2).sum():
+        return P.copy()
     G0n = G0 / nG
     P0n = P0 / nP
     A = G0n.T @ P0n
@@ -105,7 +113,8 @@ def pmpjpe_per_pose_torch(pred, gt, mean=None, std=None, dtype=None):
     P0 = p - muP
     nG = G0.pow(2).sum(dim=(1, 2), keepdim=True).sqrt()
     nP = P0.pow(2).sum(dim=(1, 2), keepdim=True).sqrt()
-    ok = ((nG > 0) & (nP > 0)).flatten()
+    ok = ((nG ** 2 > DEGENERATE_REL * g.pow(2).sum(dim=(1, 2), keepdim=True))
+          & (nP ** 2 > DEGENERATE_REL * p.pow(2).sum(dim=(1, 2), keepdim=True))).flatten()
     nGs = torch.where(nG > 0, nG, torch.ones_like(nG))
     nPs = torch.where(nP > 0, nP, torch.ones_like(nP))
     A = (G0 / nGs).transpose(1, 2) @ (P0 / nPs)
