@@ -742,6 +742,17 @@ int b200_mpjpe_pmpjpe(const float* pred, const float* gt, const float* mean, con
                      acc_cnt, true, true, stream);
 }
 
+// ReLU/dropout decisions of the last training-mode forward (tests: admit either decision for elements
+// within round-off of the ReLU kink).  out: [1024][ceil(B/32)] words, bit j of word w <-> row 32 w + j.
+int b200_debug_keep_bits(b200_plan* plan, int32_t layer, uint32_t* out, void* stream) {
+  if (!plan || !out) return fail("null argument");
+  if (layer < 0 || layer >= kNumHeavy) return fail("layer must be in [0, 5)");
+  if (plan->kind != B200_PLAN_TRAIN || !plan->u.keep[layer]) return fail("training plan required");
+  CK(cudaMemcpyAsync(out, plan->u.keep[layer], size_t(kHidden) * plan->u.ldw * 4, cudaMemcpyDeviceToDevice,
+                     (cudaStream_t)stream));
+  return 0;
+}
+
 // ---- debug GEMM: one single-phase schedule built on the fly in `scratch` (>= 64 KiB)
 int b200_debug_gemm(const uint16_t* a, const uint16_t* b, float* dmat, int32_t m, int32_t n, int32_t k, int32_t planes,
                     int32_t a_mn, int32_t b_mn, int32_t bn, void* scratch, int64_t scratch_bytes, void* stream) {

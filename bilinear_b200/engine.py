@@ -284,6 +284,16 @@ class Engine:
         return self.scalars[1]
 
 
+    def debug_keep_bits(self, layer, batch):
+        """[batch, 1024] bool: dropout keep AND (BatchNorm output > 0) of the last training forward."""
+        pl = self.plan(batch, PLAN_TRAIN)
+        ldw = (batch + 31) // 32
+        words = torch.empty(1024, ldw, dtype=torch.int32, device=self.device)
+        check(_lib.lib().b200_debug_keep_bits(pl.handle, layer, ptr(words), _stream()))
+        bits = (words.unsqueeze(-1) >> torch.arange(32, device=self.device, dtype=torch.int32)) & 1
+        return bits.reshape(1024, ldw * 32)[:, :batch].t().contiguous().bool()
+
+
 def get_engine(module):
     eng = module.__dict__.get("_b200_engine")
     if eng is None:

@@ -118,4 +118,5 @@ def test_full_size_properties(cuda_lib):
     r2 = metrics.evaluate(P2.reshape(n, 48), G.reshape(n, 48), None, None, act, 15, joints=16)
     assert float((r2.pdist - r.pdist).abs().max()) / 16 < TOL_MM
     assert abs(r2.pmpjpe - r.pmpjpe) < 1e-3
-    assert (r.pdist <= r.dist + 1e-2).all()
+    # (Procrustes minimises the sum of SQUARED distances, so pdist <= dist holds on average, not per pose)
+    assert r.pmpjpe <= r.mpjpe

@@ -53,19 +53,118 @@ def masks_tensor(masks):
     return torch.stack(masks).to(torch.uint8).cuda().contiguous()
 
 
-def check_grads(net, grads, tol, tag):
+def adopt_relu_decisions(net, masks, batch, tol_y):
+    """ReLU's derivative is discontinuous: take the CUDA path's own decisions (keep bits saved by the
+    forward) wherever they differ from the oracle's, after asserting that every such element has its
+    oracle BatchNorm output within `tol_y` of the kink (i.e. the decision is round-off either way)."""
+    from bilinear_b200.engine import get_engine
+    eng = get_engine(net)
+
+    def fn(cache):
+        out = []
+        for i, c in enumerate(cache["layers"]):
+            keep = eng.debug_keep_bits(i, batch).cpu()
+            m = masks[i].bool()
+            pos = torch.where(m, keep, c["pos"])
+            dis = pos != c["pos"]
+            if int(dis.sum()):
+                worst = float(c["y"].abs()[dis].max())
+                assert worst < tol_y, "layer %d: %d ReLU decisions differ, |y| up to %g" % (i, int(dis.sum()), worst)
+            out.append(pos)
+        return out
+    return fn
+
+
+def grad_errors(gv, grads):
     gn = float(bo.total_grad_norm(grads))
-    worst = 0.0
-    for name, p in net.named_parameters():
-        assert p.grad is not None, name
-        ref = grads[name]
+    out = {}
+    for name in bo.param_names():
         if name in ZERO_GRAD:
-            err = float((p.grad.double().cpu() - ref).norm()) / gn
+            out[name] = float((gv[name].double().cpu() - grads[name]).norm()) / gn
         else:
-            err = rel_l2(p.grad, ref)
-        worst = max(worst, err)
-        assert err < tol, "%s %s: %g" % (tag, name, err)
-    return worst
+            out[name] = rel_l2(gv[name], grads[name])
+    return out
+
+
+def adam_state_dict(st):
+    """torch.optim.Adam state_dict carrying the oracle's moments (checkpoint format, train_bilinear.py:92-104)."""
+    names = bo.param_names()
+    return {
+        "state": {i: {"step": torch.tensor(float(st.adam_step)), "exp_avg": st.m[n].float().clone(),
+                      "exp_avg_sq": st.v[n].float().clone()} for i, n in enumerate(names)},
+        "param_groups": [{"lr": 1e-3, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False,
+                          "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                          "fused": None, "decoupled_weight_decay": False, "params": list(range(len(names)))}],
+    }
+
+
+def rounding_for(precision, batch):
+    return bo.EXACT if precision == "fp32" else bo.Rounding.bf16(large_batch=batch > 256)
+
+
+# ReLU-kink tolerance on the oracle's BatchNorm output (O(1) scale): fp32 mode agrees to ~1e-6; the bf16
+# path against the bf16 restatement differs by occasional one-ulp bf16 roundings of an operand (4e-3
+# relative on one of 1024 addends)
+TOL_Y = {"fp32": 2e-5, "bf16": 2e-3}
+# CUDA vs the restatement evaluated with the SAME operand rounding
+TOL_SAME = {"fp32": 1e-5, "bf16": 2e-3}
+
+
+def adopt_relu_decisions(net, masks, batch, tol_y):
+    """ReLU's derivative is discontinuous: take the CUDA path's own decisions (keep bits saved by the
+    forward) wherever they differ from the oracle's, after asserting that every such element has its
+    oracle BatchNorm output within `tol_y` of the kink (i.e. the decision is round-off either way)."""
+    from bilinear_b200.engine import get_engine
+    eng = get_engine(net)
+
+    def fn(cache):
+        out = []
+        for i, c in enumerate(cache["layers"]):
+            keep = eng.debug_keep_bits(i, batch).cpu()
+            m = masks[i].bool()
+            pos = torch.where(m, keep, c["pos"])
+            dis = pos != c["pos"]
+            if int(dis.sum()):
+                worst = float(c["y"].abs()[dis].max())
+                assert worst < tol_y, "layer %d: %d ReLU decisions differ, |y| up to %g" % (i, int(dis.sum()), worst)
+            out.append(pos)
+        return out
+    return fn
+
+
+def grad_errors(gv, grads):
+    gn = float(bo.total_grad_norm(grads))
+    out = {}
+    for name in bo.param_names():
+        if name in ZERO_GRAD:
+            out[name] = float((gv[name].double().cpu() - grads[name]).norm()) / gn
+        else:
+            out[name] = rel_l2(gv[name], grads[name])
+    return out
+
+
+def adam_state_dict(st):
+    """torch.optim.Adam state_dict carrying the oracle's moments (checkpoint format, train_bilinear.py:92-104)."""
+    names = bo.param_names()
+    return {
+        "state": {i: {"step": torch.tensor(float(st.adam_step)), "exp_avg": st.m[n].float().clone(),
+                      "exp_avg_sq": st.v[n].float().clone()} for i, n in enumerate(names)},
+        "param_groups": [{"lr": 1e-3, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False,
+                          "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                          "fused": None, "decoupled_weight_decay": False, "params": list(range(len(names)))}],
+    }
+
+
+def rounding_for(precision, batch):
+    return bo.EXACT if precision == "fp32" else bo.Rounding.bf16(large_batch=batch > 256)
+
+
+# ReLU-kink tolerance on the oracle's BatchNorm output (O(1) scale): fp32 mode agrees to ~1e-6; the bf16
+# path against the bf16 restatement differs by occasional one-ulp bf16 roundings of an operand (4e-3
+# relative on one of 1024 addends)
+TOL_Y = {"fp32": 2e-5, "bf16": 2e-3}
+# CUDA vs the restatement evaluated with the SAME operand rounding
+TOL_SAME = {"fp32": 1e-5, "bf16": 2e-3}
 
 
 # ------------------------------------------------------------------------------------------ eval mode
@@ -82,6 +181,9 @@ def test_forward_eval(cuda_lib, precision, batch):
     assert p.shape == (batch, 48) and p.dtype == torch.float32
     err = rel_l2(p, ref)
     assert err < TOL[precision], err
+    if precision == "bf16":
+        ref16, _ = bo.forward(st, x, train=False, rnd=bo.Rounding.bf16())
+        assert rel_l2(p, ref16) < TOL_SAME["bf16"]
     # a second call with the same plan is bitwise repeatable
     with torch.no_grad():
         p2 = net(x.cuda())
@@ -93,7 +195,6 @@ def test_forward_eval(cuda_lib, precision, batch):
 @pytest.mark.parametrize("batch", [8, 64, 100, 257, 600])
 def test_forward_backward_autograd(cuda_lib, precision, batch):
     """train_bilinear.py:75-79 driven exactly like the reference: zero_grad, forward, MSELoss, backward."""
-    tol = TOL[precision]
     st = warmed_state(1)
     net, opt = make_net(1, precision, as_float_state(st))
     net.train()
@@ -104,58 +205,103 @@ def test_forward_backward_autograd(cuda_lib, precision, batch):
     p = net(x.cuda())
     loss = criterion(p, y.cuda())
     loss.backward()
+    gv = {n: q.grad for n, q in net.named_parameters()}
+    assert all(g is not None for g in gv.values())
 
-    p_ref, cache = bo.forward(st, x, train=True, masks=masks)
+    # (1) against the reference semantics (no rounding anywhere): forward quantities within the north-star
+    # tolerance; in fp32 mode the gradients too
+    st_exact = bo.State(as_float_state(st), dtype=torch.float64)
+    p_ref, cache = bo.forward(st_exact, x, train=True, masks=masks)
     loss_ref, dP = bo.mse_loss(p_ref, y)
-    grads = bo.backward(st, cache, dP)
-    assert rel_l2(p, p_ref) < tol
-    assert abs(float(loss) - float(loss_ref)) < tol * float(loss_ref)
-    check_grads(net, grads, tol * (1 if precision == "fp32" else 2), "autograd B=%d" % batch)
+    assert rel_l2(p, p_ref) < TOL[precision]
+    assert abs(float(loss.detach()) - float(loss_ref)) < TOL[precision] * float(loss_ref)
+    # (2) against the restatement with this mode's operand rounding: everything, gradients included
+    rnd = rounding_for(precision, batch)
+    st_same = bo.State(as_float_state(st), dtype=torch.float64)
+    p_same, cache = bo.forward(st_same, x, train=True, masks=masks, rnd=rnd)
+    _, dP = bo.mse_loss(p_same, y)
+    grads = bo.backward(st_same, cache, dP, rnd=rnd,
+                        relu_pos=adopt_relu_decisions(net, masks, batch, TOL_Y[precision])(cache))
+    assert rel_l2(p, p_same) < TOL_SAME[precision]
+    errs = grad_errors(gv, grads)
+    assert max(errs.values()) < TOL_SAME[precision], errs
     # BatchNorm side effects of the training-mode forward (model/bilinear.py:10)
     sd = net.state_dict()
     for i, pre in enumerate(bo.HEAVY_PREFIXES):
-        assert rel_l2(sd[pre + ".1.running_mean"], st.rm[i]) < max(tol, 1e-5)
-        assert rel_l2(sd[pre + ".1.running_var"], st.rv[i]) < max(tol, 1e-5)
-        assert int(sd[pre + ".1.num_batches_tracked"]) == st.nbt[i]
+        assert rel_l2(sd[pre + ".1.running_mean"], st_exact.rm[i]) < max(TOL[precision], 1e-5)
+        assert rel_l2(sd[pre + ".1.running_var"], st_exact.rv[i]) < max(TOL[precision], 1e-5)
+        assert int(sd[pre + ".1.num_batches_tracked"]) == st_exact.nbt[i]
+
+
+def test_bf16_gradients_against_unrounded_reference(cuda_lib):
+    """bf16 mode vs the fp32-semantics oracle: forward, loss and total gradient norm within 2e-2; the
+    per-tensor gradient error is set by flipped ReLU decisions (oracle docstring) and stays ~1e-1 with a
+    cosine above 0.99 -- the same as the CPU restatement with bf16 operand rounding shows."""
+    batch = 256
+    st = warmed_state(0)
+    net, opt = make_net(0, "bf16", as_float_state(st))
+    net.train()
+    x, y, masks = bo.synthetic_batch(17, batch)
+    net.inject_dropout_masks(masks_tensor(masks))
+    loss, gnorm = net.train_step(opt, x.cuda(), y.cuda(), update=False)
+    from bilinear_b200.engine import get_engine
+    gv = dict(zip(bo.param_names(), get_engine(net).grad_views()))
+    p_ref, cache = bo.forward(st, x, train=True, masks=masks)
+    loss_ref, dP = bo.mse_loss(p_ref, y)
+    grads = bo.backward(st, cache, dP)
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * float(loss_ref)
+    assert abs(float(gnorm) - float(bo.total_grad_norm(grads))) < 2e-2 * float(bo.total_grad_norm(grads))
+    for name in bo.param_names():
+        if name in ZERO_GRAD:
+            continue
+        a, b = gv[name].double().cpu().reshape(-1), grads[name].reshape(-1)
+        assert float(a @ b / (a.norm() * b.norm())) > 0.99, name
+        assert rel_l2(a, b) < 0.15, name
 
 
 def test_clip_and_optimizer_step_like_reference(cuda_lib):
-    """train_bilinear.py:81-83 with torch's own clip_grad_norm_ on our gradient views + optimizer.step()."""
+    """train_bilinear.py:81-83 with torch's own clip_grad_norm_ on our gradient views + optimizer.step(),
+    resuming the optimizer from a checkpoint-format state dict (model/bilinear.py:82)."""
     st = warmed_state(2)
     net, opt = make_net(2, "fp32", as_float_state(st))
+    opt.load_state_dict(adam_state_dict(st))
     net.train()
     x, y, masks = bo.synthetic_batch(13, 64)
     net.inject_dropout_masks(masks_tensor(masks))
     lr = bo.lr_schedule(1)
     for g in opt.param_groups:
         g["lr"] = lr
-    before = {k: v.clone() for k, v in net.named_parameters()}
+    before = {k: v.detach().double().cpu().clone() for k, v in net.named_parameters()}
     opt.zero_grad()
     loss = nn.MSELoss()(net(x.cuda()), y.cuda())
     loss.backward()
     norm = nn.utils.clip_grad_norm_(net.parameters(), max_norm=1)
     opt.step()
-    _, _, grads, norm_ref = bo.train_step(st, x, y, masks, lr)
+    _, _, grads, norm_ref = bo.train_step(st, x, y, masks, lr, relu_pos=adopt_relu_decisions(net, masks, 64, 2e-5))
     assert abs(float(norm) - float(norm_ref)) < 1e-5 * float(norm_ref)
     for name, p in net.named_parameters():
         if name in ZERO_GRAD:
             continue
-        delta = p.detach().double().cpu() - before[name].double().cpu()
-        delta_ref = st.p[name] - before[name].double().cpu()
-        assert float((delta - delta_ref).norm()) < 2e-3 * float(delta_ref.norm()) + 1e-7, name
+        delta = p.detach().double().cpu() - before[name]
+        delta_ref = st.p[name] - before[name]
+        assert float((delta - delta_ref).norm()) < 1e-3 * float(delta_ref.norm()) + 1e-7, name
     osd = opt.state_dict()
-    assert len(osd["state"]) == 22 and float(osd["state"][0]["step"]) == 1.0
+    assert len(osd["state"]) == 22 and float(osd["state"][0]["step"]) == 4.0
     assert rel_l2(osd["state"][2]["exp_avg"], st.m["encode.1.weight"]) < 1e-4
+    assert rel_l2(osd["state"][0]["exp_avg_sq"], st.v["encode.0.weight"]) < 1e-4
 
 
 # ------------------------------------------------------------------------------------------ fused step
 @pytest.mark.parametrize("precision,batch", [("fp32", 64), ("fp32", 2), ("fp32", 33), ("fp32", 128), ("fp32", 300),
-                                             ("bf16", 64), ("bf16", 256), ("bf16", 1000), ("bf16", 4096)])
+                                             ("fp32", 1000), ("bf16", 64), ("bf16", 256), ("bf16", 1000),
+                                             ("bf16", 4096)])
 def test_fused_train_step(cuda_lib, precision, batch):
-    """One persistent-kernel iteration of train_bilinear.py:75-83 against the oracle."""
-    tol = TOL[precision]
+    """One persistent-kernel iteration of train_bilinear.py:75-83 against the oracle (evaluated with this
+    mode's operand rounding), Adam state resumed from the oracle's."""
+    tol = TOL_SAME[precision]
     st = warmed_state(0)
     net, opt = make_net(0, precision, as_float_state(st))
+    opt.load_state_dict(adam_state_dict(st))
     net.train()
     x, y, masks = bo.synthetic_batch(17, batch)
     net.inject_dropout_masks(masks_tensor(masks))
@@ -164,32 +310,31 @@ def test_fused_train_step(cuda_lib, precision, batch):
         g["lr"] = lr
     before = {k: v.detach().double().cpu().clone() for k, v in net.named_parameters()}
     loss, gnorm = net.train_step(opt, x.cuda(), y.cuda(), max_norm=1.0)
-    p_ref, loss_ref, grads, norm_ref = bo.train_step(st, x, y, masks, lr)
     if batch == 2:
         # ill-conditioned (see tests/test_oracle_golden.py): forward-level quantities only
+        _, loss_ref, _, _ = bo.train_step(st, x, y, masks, lr)
         assert abs(float(loss) - float(loss_ref)) < 1e-2 * float(loss_ref)
         return
+    rnd = rounding_for(precision, batch)
+    p_ref, loss_ref, grads, norm_ref = bo.train_step(
+        st, x, y, masks, lr, rnd=rnd, relu_pos=adopt_relu_decisions(net, masks, batch, TOL_Y[precision]))
     assert abs(float(loss) - float(loss_ref)) < tol * float(loss_ref)
-    assert abs(float(gnorm) - float(norm_ref)) < tol * float(norm_ref) * (1 if precision == "fp32" else 2)
+    assert abs(float(gnorm) - float(norm_ref)) < tol * float(norm_ref)
     from bilinear_b200.engine import get_engine
     eng = get_engine(net)
-    gv = dict(zip([n for n, _ in net.named_parameters()], eng.grad_views()))
-    gn = float(norm_ref)
-    for name in bo.param_names():
-        if name in ZERO_GRAD:
-            err = float((gv[name].double().cpu() - grads[name]).norm()) / gn
-        else:
-            err = rel_l2(gv[name], grads[name])
-        assert err < tol * (1 if precision == "fp32" else 2), (name, err)
-    mtol = 2e-3 if precision == "fp32" else 5e-2
+    names = [n for n, _ in net.named_parameters()]
+    assert names == bo.param_names()
+    errs = grad_errors(dict(zip(names, eng.grad_views())), grads)
+    assert max(errs.values()) < tol, errs
+    # parameter update: Adam divides by sqrt(v) -- a relative gradient error e becomes a relative
+    # update error ~e, except where |g| ~ eps
     for name, p in net.named_parameters():
         if name in ZERO_GRAD:
             continue
         delta = p.detach().double().cpu() - before[name]
         delta_ref = st.p[name] - before[name]
-        assert float((delta - delta_ref).norm()) < mtol * float(delta_ref.norm()) + 1e-7, name
+        assert float((delta - delta_ref).norm()) < 100 * tol * float(delta_ref.norm()) + 1e-7, name
     m, v = eng.state_views()
-    names = [n for n, _ in net.named_parameters()]
     for name, mi, vi in zip(names, m, v):
         if name in ZERO_GRAD:
             continue
@@ -200,6 +345,7 @@ def test_fused_train_step(cuda_lib, precision, batch):
         assert rel_l2(sd[pre + ".1.running_mean"], st.rm[i]) < max(tol, 1e-5)
         assert rel_l2(sd[pre + ".1.running_var"], st.rv[i]) < max(tol, 1e-5)
         assert int(sd[pre + ".1.num_batches_tracked"]) == st.nbt[i]
+    assert float(opt.state_dict()["state"][0]["step"]) == 4.0
 
 
 def test_fused_multi_step_trajectory(cuda_lib):
