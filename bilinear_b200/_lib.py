@@ -64,6 +64,7 @@ _SIGS = {
     "b200_pmpjpe": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 4),
     "b200_mpjpe_pmpjpe": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 6),
     "b200_debug_keep_bits": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200_debug_phase_ns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "b200_debug_gemm": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 7 + [C.c_void_p, C.c_int64, C.c_void_p]),
     "b200_debug_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
 }

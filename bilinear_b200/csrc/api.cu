@@ -129,6 +129,7 @@ constexpr int kMaxTmaps = 128, kMaxGemm = 64, kMaxEw = 64, kMaxPhases = 128;
 
 struct Bufs {
   CUtensorMap* tmaps; GemmJob* gjobs; EwJob* ejobs; Phase* phases; unsigned int* barrier;
+  unsigned long long* phase_ns;
   uint8_t* acc_base; int64_t acc_bytes;
   double* loss_acc; double* gnorm2; double* stats_f[kNumHeavy]; double* stats_b[kNumHeavy];
   float* save_mean[kNumHeavy]; float* save_rstd[kNumHeavy]; float* scale[kNumHeavy]; float* shift[kNumHeavy];
@@ -162,6 +163,7 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
   u.ejobs = c.take_n<EwJob>(kMaxEw);
   u.phases = c.take_n<Phase>(kMaxPhases);
   u.barrier = c.take_n<unsigned int>(64);
+  u.phase_ns = c.take_n<unsigned long long>(kMaxPhases + 1);
   // accumulators cleared at the start of every step (one contiguous region)
   const int64_t acc0 = (c.off + 1023) & ~int64_t(1023);
   u.loss_acc = c.take_n<double>(16);
@@ -229,6 +231,7 @@ struct b200_plan {
   Sched s_refresh, s_eval, s_fwd, s_bwd, s_step, s_update;
   bool phase_open = false;
   Phase cur;
+  int last_first = 0, last_count = 0;
 };
 
 static int add_map(b200_plan* pl, const PlaneRef& r, int64_t inner, int64_t rows, int box_rows, int* idx) {
@@ -569,6 +572,8 @@ static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, c
   p.phases = pl->u.phases + s.first;
   p.tmaps = pl->u.tmaps;
   p.barrier = pl->u.barrier;
+  p.phase_ns = pl->u.phase_ns;
+  pl->last_first = s.first; pl->last_count = count;
   p.num_phases = count;
   p.dyn = dyn;
   const bool coop = count > 1;
@@ -750,6 +755,25 @@ int b200_debug_keep_bits(b200_plan* plan, int32_t layer, uint32_t* out, void* st
   if (plan->kind != B200_PLAN_TRAIN || !plan->u.keep[layer]) return fail("training plan required");
   CK(cudaMemcpyAsync(out, plan->u.keep[layer], size_t(kHidden) * plan->u.ldw * 4, cudaMemcpyDeviceToDevice,
                      (cudaStream_t)stream));
+  return 0;
+}
+
+// Per-phase durations (ns) of the most recent launch of this plan; synchronises the device.
+// kinds_out[i]: 0 = GEMM phase (value = number of tiles in tiles_out[i]), else 1 + EwKind of its first job.
+int b200_debug_phase_ns(b200_plan* plan, int64_t* ns_out, int32_t* kinds_out, int32_t* tiles_out, int32_t max_phases,
+                        int32_t* count_out) {
+  if (!plan || !ns_out || !count_out) return fail("null argument");
+  CK(cudaDeviceSynchronize());
+  std::vector<unsigned long long> t(plan->last_count + 1);
+  CK(cudaMemcpy(t.data(), plan->u.phase_ns, t.size() * 8, cudaMemcpyDeviceToHost));
+  const int n = std::min(plan->last_count, max_phases);
+  for (int i = 0; i < n; ++i) {
+    ns_out[i] = int64_t(t[i + 1] - t[i]);
+    const Phase& ph = plan->ph[plan->last_first + i];
+    if (kinds_out) kinds_out[i] = ph.gemm_tiles > 0 ? 0 : 1 + plan->ej[ph.first_ew].kind;
+    if (tiles_out) tiles_out[i] = ph.gemm_tiles > 0 ? (ph.gemm_tiles | (plan->gj[ph.first_gemm].epi << 24)) : ph.num_ew;
+  }
+  *count_out = n;
   return 0;
 }
 

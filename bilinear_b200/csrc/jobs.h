@@ -166,6 +166,7 @@ struct MegaParams {
   const Phase* phases;
   const void* tmaps;        // array of CUtensorMap (128 B each, 64 B aligned)
   unsigned int* barrier;    // grid barrier counter (zeroed before launch)
+  unsigned long long* phase_ns;  // [num_phases + 1] globaltimer stamps written by block 0 (nullptr: off)
   int32_t num_phases;
   int32_t pad;
   Dyn dyn;

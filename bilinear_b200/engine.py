@@ -284,6 +284,17 @@ class Engine:
         return self.scalars[1]
 
 
+    def debug_phase_ns(self, batch, kind=PLAN_TRAIN):
+        """[(duration_ns, kind, tiles)] per phase of the last launch on the plan for `batch`."""
+        pl = self.plan(batch, kind)
+        n = 160
+        ns = (C.c_int64 * n)()
+        kinds = (C.c_int32 * n)()
+        tiles = (C.c_int32 * n)()
+        cnt = C.c_int32(0)
+        check(_lib.lib().b200_debug_phase_ns(pl.handle, ns, kinds, tiles, n, C.byref(cnt)))
+        return [(int(ns[i]), int(kinds[i]), int(tiles[i])) for i in range(cnt.value)]
+
     def debug_keep_bits(self, layer, batch):
         """[batch, 1024] bool: dropout keep AND (BatchNorm output > 0) of the last training forward."""
         pl = self.plan(batch, PLAN_TRAIN)

@@ -150,6 +150,11 @@ int64_t b200_launch_count(void);
 /* keep bits (dropout keep AND BatchNorm output > 0) of heavy layer `layer` from the last
  * training-mode forward of this plan: out [1024][ceil(B/32)] uint32, bit j of word w <-> row 32 w + j */
 int b200_debug_keep_bits(b200_plan* plan, int32_t layer, uint32_t* out, void* stream);
+/* per-phase durations (ns, from %globaltimer stamps) of the most recent launch on this plan; HOST
+ * output arrays; synchronises the device.  kinds_out: 0 = GEMM phase, else 1 + elementwise kind;
+ * tiles_out: GEMM tiles | epilogue kind << 24, or number of elementwise jobs. */
+int b200_debug_phase_ns(b200_plan* plan, int64_t* ns_out, int32_t* kinds_out, int32_t* tiles_out, int32_t max_phases,
+                        int32_t* count_out);
 /* D[M][N] (fp32, ld = N) = A * B^T on the tcgen05 path.  Operands are bf16 plane tensors:
  *   a_mn == 0: A is [planes][M][K] (K contiguous);  a_mn == 1: A is [planes][K][M] (M contiguous)
  *   likewise for B with N.  bn = tile width (multiple of 16, <= 256; multiple of 64 if b_mn). */

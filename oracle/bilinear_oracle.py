@@ -55,13 +55,15 @@ BN_EPS = 1e-5
 class Rounding:
     """Where values are rounded to bfloat16 (None = nowhere: the reference's fp32 semantics)."""
 
-    def __init__(self, operands=False, saved_z=False, saved_dy=False):
-        self.operands, self.saved_z, self.saved_dy = operands, saved_z, saved_dy
+    def __init__(self, operands=False, saved_z=False, saved_dy=False, fwd_z=False):
+        self.operands, self.saved_z, self.saved_dy, self.fwd_z = operands, saved_z, saved_dy, fwd_z
 
     @staticmethod
     def bf16(large_batch=False):
-        # large_batch: the two-pass BatchNorm backward (B > 256) also keeps dy in bf16 between passes
-        return Rounding(operands=True, saved_z=True, saved_dy=large_batch)
+        # large_batch (B > 256): BatchNorm needs the whole column before any element can be normalised,
+        # so z (forward) and dy (backward) make one round trip through HBM between the two passes -- in
+        # bf16; the normalisation then starts from the rounded z
+        return Rounding(operands=True, saved_z=True, saved_dy=large_batch, fwd_z=large_batch)
 
     @staticmethod
     def _r(t):
@@ -163,7 +165,7 @@ def _heavy_forward(st, i, h, train, mask, momentum, rnd=EXACT):
     else:
         mean, var = st.rm[i], st.rv[i]
     rstd = 1.0 / torch.sqrt(var + BN_EPS)
-    xhat = (z - mean) * rstd
+    xhat = ((rnd.z(z) if (train and rnd.fwd_z) else z) - mean) * rstd
     y = g * xhat + be                                   # nn.BatchNorm1d (affine)
     a = torch.clamp(y, min=0)                           # nn.ReLU
     if train:

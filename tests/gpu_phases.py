@@ -1,0 +1,57 @@
+"""Per-phase timing of the persistent kernel (not a pytest module): python tests/gpu_phases.py fp32:64 bf16:65536"""
+import os
+import sys
+import warnings
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from bilinear_b200.engine import get_engine
+from bilinear_b200._lib import PLAN_INFER, PLAN_TRAIN
+from bilinear_b200.model import bilinear as mb
+
+EPI = ["STORE", "FWD_SMALL", "FWD_LARGE", "FWD_EVAL", "DECODE", "DGRAD_SMALL", "DGRAD_LARGE", "WGRAD"]
+EW = ["PREP", "DROPBITS", "BN_FOLD", "BN_FWD_APPLY", "BN_BWD_APPLY", "SPLIT_DP", "SUMSQ", "ADAM", "SPLIT_W"]
+
+
+def show(tag, ph):
+    tot = sum(p[0] for p in ph)
+    print("== %s: %d phases, %.1f us total" % (tag, len(ph), tot / 1e3))
+    for i, (ns, kind, tiles) in enumerate(ph):
+        if kind == 0:
+            name = "GEMM %-12s tiles=%d" % (EPI[tiles >> 24], tiles & 0xffffff)
+        else:
+            name = "EW   %-12s jobs=%d" % (EW[kind - 1], tiles)
+        print("   %2d %-34s %9.1f us" % (i, name, ns / 1e3))
+    sys.stdout.flush()
+
+
+def main():
+    cases = sys.argv[1:] or ["fp32:64", "bf16:64", "bf16:65536"]
+    for c in cases:
+        prec, b = c.split(":")
+        b = int(b)
+        torch.manual_seed(0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            net, opt, _, _ = mb.load(torch.device("cuda"))
+        net.set_precision(prec)
+        net.train()
+        x = torch.randn(b, 32, device="cuda")
+        y = torch.randn(b, 48, device="cuda")
+        for _ in range(3):
+            net.train_step(opt, x, y)
+        torch.cuda.synchronize()
+        eng = get_engine(net)
+        show("train_step %s B=%d" % (prec, b), eng.debug_phase_ns(b))
+        net.eval()
+        with torch.no_grad():
+            for _ in range(2):
+                net(x)
+        show("forward_eval %s B=%d" % (prec, b), eng.debug_phase_ns(b))
+        del net, opt, eng
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
