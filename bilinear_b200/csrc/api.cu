@@ -134,12 +134,12 @@ struct Bufs {
   double* loss_acc; double* gnorm2; double* stats_f[kNumHeavy]; double* stats_b[kNumHeavy];
   float* save_mean[kNumHeavy]; float* save_rstd[kNumHeavy]; float* scale[kNumHeavy]; float* shift[kNumHeavy];
   PlaneRef W[kNumLinear], WT[kNumLinear];
-  PlaneRef X_bm, X_fm;
+  PlaneRef X_fm;
   void* zT[kNumHeavy]; void* dyT[kNumHeavy];
   uint32_t* keep[kNumHeavy]; uint32_t* drop;
-  PlaneRef h_bm[kNumHeavy], h_fm[kNumHeavy], dz_bm[kNumHeavy], dz_fm[kNumHeavy];
+  PlaneRef h_fm[kNumHeavy], dz_fm[kNumHeavy];
   float* G2; float* G4;
-  PlaneRef dP_bm, dP_fm;
+  PlaneRef dP_fm;
   int64_t Bs, ldw;
 };
 
@@ -163,7 +163,7 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
   u.ejobs = c.take_n<EwJob>(kMaxEw);
   u.phases = c.take_n<Phase>(kMaxPhases);
   u.barrier = c.take_n<unsigned int>(64);
-  u.phase_ns = c.take_n<unsigned long long>(kMaxPhases + 1);
+  u.phase_ns = c.take_n<unsigned long long>(8 * (kMaxPhases + 1));
   // accumulators cleared at the start of every step (one contiguous region)
   const int64_t acc0 = (c.off + 1023) & ~int64_t(1023);
   u.loss_acc = c.take_n<double>(16);
@@ -182,32 +182,28 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
     if (train && l >= 1) u.WT[l] = take_planes(c, P, kPL.cols[l], kPL.rows[l]);
     else u.WT[l] = PlaneRef{nullptr, 0, 0};
   }
-  u.X_bm = take_planes(c, P, B, kDin);
-  u.X_fm = train ? take_planes(c, P, kDin, Bs) : PlaneRef{nullptr, 0, 0};
+  u.X_fm = take_planes(c, P, kDin, Bs);
   const int64_t zbytes = int64_t(kHidden) * Bs * (P == 1 ? 2 : 4);
   u.drop = train ? c.take_n<uint32_t>(int64_t(kNumHeavy) * kHidden * ldw) : nullptr;
   for (int l = 0; l < kNumHeavy; ++l) {
-    u.h_bm[l] = take_planes(c, P, B, kHidden);
-    u.h_fm[l] = (train || l == 0 || l == 2) ? take_planes(c, P, kHidden, Bs) : PlaneRef{nullptr, 0, 0};
+    u.h_fm[l] = take_planes(c, P, kHidden, Bs);
     if (train) {
       u.zT[l] = c.take(zbytes);
       u.dyT[l] = large ? c.take(zbytes) : nullptr;
       u.keep[l] = c.take_n<uint32_t>(int64_t(kHidden) * ldw);
-      u.dz_bm[l] = take_planes(c, P, B, kHidden);
       u.dz_fm[l] = take_planes(c, P, kHidden, Bs);
     } else {
       u.zT[l] = u.dyT[l] = nullptr; u.keep[l] = nullptr;
-      u.dz_bm[l] = u.dz_fm[l] = PlaneRef{nullptr, 0, 0};
+      u.dz_fm[l] = PlaneRef{nullptr, 0, 0};
     }
   }
   if (train) {
     u.G2 = c.take_n<float>(int64_t(kHidden) * Bs);
     u.G4 = c.take_n<float>(int64_t(kHidden) * Bs);
-    u.dP_bm = take_planes(c, P, B, kDout);
     u.dP_fm = take_planes(c, P, kDout, Bs);
   } else {
     u.G2 = u.G4 = nullptr;
-    u.dP_bm = u.dP_fm = PlaneRef{nullptr, 0, 0};
+    u.dP_fm = PlaneRef{nullptr, 0, 0};
   }
   c.take(0);
   return c.off + 1024;
@@ -277,13 +273,17 @@ static Args base_args(const b200_plan* pl, int layer) {
   return a;
 }
 
-static int add_gemm(b200_plan* pl, const PlaneRef& A, int64_t a_inner, int64_t a_rows, const PlaneRef& Bop,
-                    int64_t b_inner, int64_t b_rows, int M, int N, int K, int BN, int epi, const Args& a) {
+// D[m][n] = sum_k A[m][k] B[n][k].  K-major operand: global [rows = m|n][inner = k];
+// MN-major operand (x_mn = 1): global [rows = k][inner = m|n] -- the feature-major activations.
+static int add_gemm(b200_plan* pl, const PlaneRef& A, int a_mn, const PlaneRef& Bop, int b_mn, int M, int N, int K,
+                    int BN, int epi, const Args& a) {
   if (int(pl->gj.size()) >= kMaxGemm) return fail("too many gemm jobs");
+  if (b_mn && BN % 64) return fail("MN-major B operand needs a tile width that is a multiple of 64");
   GemmJob g;
   memset(&g, 0, sizeof g);
-  if (add_map(pl, A, a_inner, a_rows, 128, &g.tmap_a)) return 1;
-  if (add_map(pl, Bop, b_inner, b_rows, BN, &g.tmap_b)) return 1;
+  if (a_mn ? add_map(pl, A, M, K, 64, &g.tmap_a) : add_map(pl, A, K, M, 128, &g.tmap_a)) return 1;
+  if (b_mn ? add_map(pl, Bop, N, K, 64, &g.tmap_b) : add_map(pl, Bop, K, N, BN, &g.tmap_b)) return 1;
+  g.a_mn = a_mn; g.b_mn = b_mn;
   g.M = M; g.N = N; g.K = K; g.BN = BN;
   g.m_tiles = (M + 127) / 128;
   g.n_tiles = (N + BN - 1) / BN;
@@ -317,7 +317,14 @@ static Args adam_args(const b200_plan* pl) {
   return a;
 }
 
+// tile width over the batch dimension (activations are the MN-major B operand: multiples of 64)
 static int tile_bn(const b200_plan* pl, int n) {
+  const int cap = (pl->P == 1) ? 256 : 128;
+  const int r = (n + 63) & ~63;
+  return std::min(cap, r);
+}
+// tile width over a feature dimension (K-major B operand of the wgrad GEMMs)
+static int tile_bn_feat(const b200_plan* pl, int n) {
   const int cap = (pl->P == 1) ? 256 : 128;
   const int r = (n + 15) & ~15;
   return std::min(cap, r);
@@ -341,14 +348,13 @@ static int build_fwd_layer(b200_plan* pl, int l, bool train) {
   a.drop = u.drop ? u.drop + int64_t(l) * kHidden * u.ldw : nullptr;
   if (l == 2) a.skip_fm = u.h_fm[0];
   if (l == 4) a.skip_fm = u.h_fm[2];
-  a.out_bm = u.h_bm[l];
   a.out_fm = u.h_fm[l];
-  const PlaneRef& in = (l == 0) ? u.X_bm : u.h_bm[l - 1];
+  const PlaneRef& in = (l == 0) ? u.X_fm : u.h_fm[l - 1];
   const int K = kPL.cols[l];
   const int BN = tile_bn(pl, B);
   const int epi = !train ? EPI_FWD_EVAL : (pl->large ? EPI_FWD_LARGE : EPI_FWD_SMALL);
   begin_phase(pl);
-  if (add_gemm(pl, u.W[l], K, kHidden, in, K, B, kHidden, B, K, BN, epi, a)) return 1;
+  if (add_gemm(pl, u.W[l], 0, in, 1, kHidden, B, K, BN, epi, a)) return 1;
   end_phase(pl);
   if (train && pl->large) {
     begin_phase(pl);
@@ -365,12 +371,9 @@ static int build_decode(b200_plan* pl, bool fuse_loss) {
   a.fuse_loss = fuse_loss ? 1 : 0;
   a.loss_acc = u.loss_acc;
   a.grad_bias = pl->d.grads ? pl->d.grads + kPL.b[5] : nullptr;
-  a.out_bm = u.dP_bm;
   a.out_fm = u.dP_fm;
   begin_phase(pl);
-  if (add_gemm(pl, u.W[5], kHidden, kDout, u.h_bm[4], kHidden, pl->B, kDout, pl->B, kHidden, tile_bn(pl, pl->B),
-               EPI_DECODE, a))
-    return 1;
+  if (add_gemm(pl, u.W[5], 0, u.h_fm[4], 1, kDout, pl->B, kHidden, tile_bn(pl, pl->B), EPI_DECODE, a)) return 1;
   end_phase(pl);
   return 0;
 }
@@ -390,7 +393,6 @@ static int build_backward(b200_plan* pl, bool with_norm) {
     a.stats = u.stats_b[l];
     a.skip_in = (l == 2) ? u.G4 : (l == 0 ? u.G2 : nullptr);
     a.g_out = (l == 4) ? u.G4 : (l == 2 ? u.G2 : nullptr);
-    a.out_bm = u.dz_bm[l];
     a.out_fm = u.dz_fm[l];
     a.grad_bias = d.grads + kPL.b[l];
     a.grad_gamma = d.grads + kPL.g[l];
@@ -398,10 +400,9 @@ static int build_backward(b200_plan* pl, bool with_norm) {
     a.gnorm2 = with_norm ? u.gnorm2 : nullptr;
     const int up = l + 1;                      // the Linear whose input is h_l
     const int Kd = kPL.rows[up];               // 1024, or 48 for decode
-    const PlaneRef& dzu = (up == 5) ? u.dP_bm : u.dz_bm[up];
+    const PlaneRef& dzu = (up == 5) ? u.dP_fm : u.dz_fm[up];
     begin_phase(pl);
-    if (add_gemm(pl, u.WT[up], Kd, kHidden, dzu, Kd, B, kHidden, B, Kd, tile_bn(pl, B),
-                 pl->large ? EPI_DGRAD_LARGE : EPI_DGRAD_SMALL, a))
+    if (add_gemm(pl, u.WT[up], 0, dzu, 1, kHidden, B, Kd, tile_bn(pl, B), pl->large ? EPI_DGRAD_LARGE : EPI_DGRAD_SMALL, a))
       return 1;
     {  // wgrad of Linear `up`: dW[out][in] = sum_b dz[b][out] h_l[b][in]
       Args w = base_args(pl, up);
@@ -409,9 +410,7 @@ static int build_backward(b200_plan* pl, bool with_norm) {
       w.ld_out = kHidden;
       w.gnorm2 = with_norm ? u.gnorm2 : nullptr;
       const PlaneRef& dzT = (up == 5) ? u.dP_fm : u.dz_fm[up];
-      if (add_gemm(pl, dzT, B, kPL.rows[up], u.h_fm[l], B, kHidden, kPL.rows[up], kHidden, B, tile_bn(pl, kHidden),
-                   EPI_WGRAD, w))
-        return 1;
+      if (add_gemm(pl, dzT, 0, u.h_fm[l], 0, kPL.rows[up], kHidden, B, tile_bn_feat(pl, kHidden), EPI_WGRAD, w)) return 1;
     }
     end_phase(pl);
     if (pl->large) {
@@ -426,7 +425,7 @@ static int build_backward(b200_plan* pl, bool with_norm) {
     w.out_f32 = d.grads + kPL.w[0];
     w.ld_out = kDin;
     w.gnorm2 = with_norm ? u.gnorm2 : nullptr;
-    if (add_gemm(pl, u.dz_fm[0], B, kHidden, u.X_fm, B, kDin, kHidden, kDin, B, 32, EPI_WGRAD, w)) return 1;
+    if (add_gemm(pl, u.dz_fm[0], 0, u.X_fm, 0, kHidden, kDin, B, 32, EPI_WGRAD, w)) return 1;
   }
   end_phase(pl);
   return 0;
@@ -467,7 +466,7 @@ static int build_plan(b200_plan* pl) {
   }
   {
     Args a = base_args(pl, 0);
-    a.src = SRC_X; a.src_cols = kDin; a.out_bm = u.X_bm;
+    a.src = SRC_X; a.src_cols = kDin; a.out_fm = u.X_fm;
     if (add_ew(pl, EW_PREP, a)) return 1;
   }
   end_phase(pl);
@@ -480,7 +479,7 @@ static int build_plan(b200_plan* pl) {
   auto prep_fwd = [&](bool zero_grads) -> int {
     begin_phase(pl);
     Args a = base_args(pl, 0);
-    a.src = SRC_X; a.src_cols = kDin; a.out_bm = u.X_bm; a.out_fm = u.X_fm;
+    a.src = SRC_X; a.src_cols = kDin; a.out_fm = u.X_fm;
     zero_list_step(pl, a, true, zero_grads);
     for (int l = 0; l < kNumHeavy; ++l) a.nbt_w[l] = d.num_batches_tracked[l];
     if (add_ew(pl, EW_PREP, a)) return 1;
@@ -514,7 +513,7 @@ static int build_plan(b200_plan* pl) {
       if (add_ew(pl, EW_PREP, z)) return 1;
     }
     Args s = base_args(pl, 5);
-    s.out_bm = u.dP_bm; s.out_fm = u.dP_fm; s.grad_bias = d.grads + kPL.b[5];
+    s.out_fm = u.dP_fm; s.grad_bias = d.grads + kPL.b[5];
     if (add_ew(pl, EW_SPLIT_DP, s)) return 1;
   }
   end_phase(pl);
@@ -764,11 +763,14 @@ int b200_debug_phase_ns(b200_plan* plan, int64_t* ns_out, int32_t* kinds_out, in
                         int32_t* count_out) {
   if (!plan || !ns_out || !count_out) return fail("null argument");
   CK(cudaDeviceSynchronize());
-  std::vector<unsigned long long> t(plan->last_count + 1);
+  std::vector<unsigned long long> t(8 * (plan->last_count + 1));
   CK(cudaMemcpy(t.data(), plan->u.phase_ns, t.size() * 8, cudaMemcpyDeviceToHost));
   const int n = std::min(plan->last_count, max_phases);
   for (int i = 0; i < n; ++i) {
-    ns_out[i] = int64_t(t[i + 1] - t[i]);
+    // 8 values per phase: total duration, then offsets from the phase start of: producer start,
+    // producer done, MMA issue done, first accumulator ready, epilogue done, work done (block 0), spare
+    ns_out[8 * i] = int64_t(t[8 * (i + 1)] - t[8 * i]);
+    for (int k = 1; k < 8; ++k) ns_out[8 * i + k] = t[8 * i + k] >= t[8 * i] ? int64_t(t[8 * i + k] - t[8 * i]) : -1;
     const Phase& ph = plan->ph[plan->last_first + i];
     if (kinds_out) kinds_out[i] = ph.gemm_tiles > 0 ? 0 : 1 + plan->ej[ph.first_ew].kind;
     if (tiles_out) tiles_out[i] = ph.gemm_tiles > 0 ? (ph.gemm_tiles | (plan->gj[ph.first_gemm].epi << 24)) : ph.num_ew;

@@ -36,12 +36,12 @@ enum EpiKind : int32_t {
 };
 
 enum EwKind : int32_t {
-  EW_PREP = 0,         // zero accumulators, split x into planes (+transposed), bump BN counters
+  EW_PREP = 0,         // zero accumulators, split x into feature-major planes, bump BN counters
   EW_DROPBITS = 1,     // pack injected uint8 masks / generate Philox bits -> [f][b/32] words
   EW_BN_FOLD = 2,      // eval: scale = g*rsqrt(rv+eps), shift = b + (bias-rm)*scale
-  EW_BN_FWD_APPLY = 3, // large path: z -> h (both layouts) + keep bits + running stats
-  EW_BN_BWD_APPLY = 4, // large path: dy,z -> dz (both layouts) + db
-  EW_SPLIT_DP = 5,     // external dP [B][48] fp32 -> planes (both layouts) + db5 (autograd path)
+  EW_BN_FWD_APPLY = 3, // large path: z -> h + keep bits + running stats
+  EW_BN_BWD_APPLY = 4, // large path: dy,z -> dz + db
+  EW_SPLIT_DP = 5,     // external dP [B][48] fp32 -> feature-major planes + db5 (autograd path)
   EW_SUMSQ = 6,        // sum of squares of the flat gradient (data-parallel path, after allreduce)
   EW_ADAM = 7,         // clip coefficient + Adam + refresh bf16 operand planes of the weights
   EW_SPLIT_W = 8,      // fp32 master weights -> bf16 operand planes (both layouts), no update
@@ -76,7 +76,7 @@ enum DynSrc : int32_t { SRC_NONE = 0, SRC_X = 1, SRC_DP = 2 };
 
 constexpr int kMaxZero = 8;
 
-struct Args {
+struct alignas(16) Args {
   // ---- generic
   int32_t layer;           // 0..5
   int32_t planes;          // 1 | 3
@@ -108,9 +108,9 @@ struct Args {
   const float* skip_in;    // dgrad: gradient arriving over the residual edge  [f][ldT] (nullptr: none)
   float* g_out;            // dgrad: total gradient at this layer's output, kept for a later skip
   PlaneRef skip_fm;        // fwd: residual input, feature-major planes (p == nullptr: none)
-  // ---- plane outputs
-  PlaneRef out_bm;         // batch-major   [b][f]
-  PlaneRef out_fm;         // feature-major [f][b]
+  // ---- plane output: feature-major [f][b] (every activation / gradient operand lives in this one
+  // layout: K-major A operand of the wgrad GEMMs, MN-major B operand of the forward / dgrad GEMMs)
+  PlaneRef out_fm;
   // ---- decode / loss
   double* loss_acc;        // sum (p-y)^2
   float* grad_bias;        // db   (decode: [48]; heavy: [M])
@@ -134,9 +134,11 @@ struct Args {
   int32_t w_cols[kNumLinear];
   PlaneRef w_planes[kNumLinear];   // [out][in]
   PlaneRef wT_planes[kNumLinear];  // [in][out]  (p == nullptr: not maintained)
+  int32_t adam_tile_base[kNumLinear + 1];  // prefix sums of 64x64 tiles per weight matrix (EW_ADAM)
+  int32_t pad_[1];
 };
 
-struct GemmJob {
+struct alignas(16) GemmJob {
   int32_t tmap_a, tmap_b;  // indices into the tensor-map table
   int32_t a_mn, b_mn;      // 1: operand is MN-major in shared memory (global layout [k][mn])
   int32_t M, N, K;
@@ -146,7 +148,7 @@ struct GemmJob {
   Args a;
 };
 
-struct EwJob {
+struct alignas(16) EwJob {
   int32_t kind;
   int32_t pad;
   Args a;

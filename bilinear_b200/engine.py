@@ -288,12 +288,13 @@ class Engine:
         """[(duration_ns, kind, tiles)] per phase of the last launch on the plan for `batch`."""
         pl = self.plan(batch, kind)
         n = 160
-        ns = (C.c_int64 * n)()
+        ns = (C.c_int64 * (8 * n))()
         kinds = (C.c_int32 * n)()
         tiles = (C.c_int32 * n)()
         cnt = C.c_int32(0)
         check(_lib.lib().b200_debug_phase_ns(pl.handle, ns, kinds, tiles, n, C.byref(cnt)))
-        return [(int(ns[i]), int(kinds[i]), int(tiles[i])) for i in range(cnt.value)]
+        return [(int(ns[8 * i]), int(kinds[i]), int(tiles[i]), [int(ns[8 * i + k]) for k in range(1, 7)])
+                for i in range(cnt.value)]
 
     def debug_keep_bits(self, layer, batch):
         """[batch, 1024] bool: dropout keep AND (BatchNorm output > 0) of the last training forward."""

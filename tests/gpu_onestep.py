@@ -1,0 +1,26 @@
+"""A handful of fused training iterations (ncu target; not a pytest module):
+python tests/gpu_onestep.py [fp32|bf16] [batch] [iters]"""
+import os
+import sys
+import warnings
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from bilinear_b200.model import bilinear as mb
+
+prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+b = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+torch.manual_seed(0)
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    net, opt, _, _ = mb.load(torch.device("cuda"))
+net.set_precision(prec)
+net.train()
+x = torch.randn(b, 32, device="cuda")
+y = torch.randn(b, 48, device="cuda")
+for _ in range(iters):
+    loss, gn = net.train_step(opt, x, y)
+torch.cuda.synchronize()
+print("ok loss %.5f gnorm %.4f" % (float(loss), float(gn)))

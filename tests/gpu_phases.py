@@ -17,12 +17,13 @@ EW = ["PREP", "DROPBITS", "BN_FOLD", "BN_FWD_APPLY", "BN_BWD_APPLY", "SPLIT_DP",
 def show(tag, ph):
     tot = sum(p[0] for p in ph)
     print("== %s: %d phases, %.1f us total" % (tag, len(ph), tot / 1e3))
-    for i, (ns, kind, tiles) in enumerate(ph):
+    for i, (ns, kind, tiles, sub) in enumerate(ph):
         if kind == 0:
             name = "GEMM %-12s tiles=%d" % (EPI[tiles >> 24], tiles & 0xffffff)
         else:
             name = "EW   %-12s jobs=%d" % (EW[kind - 1], tiles)
-        print("   %2d %-34s %9.1f us" % (i, name, ns / 1e3))
+        print("   %2d %-34s %9.1f us   [prod0 %s prodEnd %s mmaEnd %s acc0 %s epiEnd %s work %s]" %
+              ((i, name, ns / 1e3) + tuple("%.1f" % (s / 1e3) if s >= 0 else "-" for s in sub)))
     sys.stdout.flush()
 
 
