@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
+#include <queue>
 #include <atomic>
 #include <cmath>
 #include <string>
@@ -125,15 +127,19 @@ struct Carver {
   template <class T> T* take_n(int64_t n) { return reinterpret_cast<T*>(take(n * int64_t(sizeof(T)))); }
 };
 
-constexpr int kMaxTmaps = 128, kMaxGemm = 64, kMaxEw = 64, kMaxPhases = 128;
+constexpr int kMaxTmaps = 128, kMaxGemm = 64, kMaxEw = 96, kMaxPhases = 160;
+constexpr int kMaxSched = 1 << 18;   // int32 entries of per-phase tile schedules
+constexpr int kSmallSplit = 16;      // K slices of the small-batch GEMMs (K = 1024 -> one k-block each)
 
 struct Bufs {
   CUtensorMap* tmaps; GemmJob* gjobs; EwJob* ejobs; Phase* phases; unsigned int* barrier;
   unsigned long long* phase_ns;
+  int32_t* sched; AdamTab* adam_tab;
+  float* part;                       // small path: [kSmallSplit][1024][Bs] fp32 partial sums
   uint8_t* acc_base; int64_t acc_bytes;
   double* loss_acc; double* gnorm2; double* stats_f[kNumHeavy]; double* stats_b[kNumHeavy];
   float* save_mean[kNumHeavy]; float* save_rstd[kNumHeavy]; float* scale[kNumHeavy]; float* shift[kNumHeavy];
-  PlaneRef W[kNumLinear], WT[kNumLinear];
+  PlaneRef W[kNumLinear];
   PlaneRef X_fm;
   void* zT[kNumHeavy]; void* dyT[kNumHeavy];
   uint32_t* keep[kNumHeavy]; uint32_t* drop;
@@ -164,6 +170,9 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
   u.phases = c.take_n<Phase>(kMaxPhases);
   u.barrier = c.take_n<unsigned int>(64);
   u.phase_ns = c.take_n<unsigned long long>(8 * (kMaxPhases + 1));
+  u.sched = c.take_n<int32_t>(kMaxSched);
+  u.adam_tab = c.take_n<AdamTab>(1);
+  u.part = large ? nullptr : c.take_n<float>(int64_t(kSmallSplit) * kHidden * Bs);
   // accumulators cleared at the start of every step (one contiguous region)
   const int64_t acc0 = (c.off + 1023) & ~int64_t(1023);
   u.loss_acc = c.take_n<double>(16);
@@ -179,8 +188,6 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
   }
   for (int l = 0; l < kNumLinear; ++l) {
     u.W[l] = take_planes(c, P, kPL.rows[l], kPL.cols[l]);
-    if (train && l >= 1) u.WT[l] = take_planes(c, P, kPL.cols[l], kPL.rows[l]);
-    else u.WT[l] = PlaneRef{nullptr, 0, 0};
   }
   u.X_fm = take_planes(c, P, kDin, Bs);
   const int64_t zbytes = int64_t(kHidden) * Bs * (P == 1 ? 2 : 4);
@@ -224,6 +231,7 @@ struct b200_plan {
   std::vector<GemmJob> gj;
   std::vector<EwJob> ej;
   std::vector<Phase> ph;
+  std::vector<int32_t> sched;
   Sched s_refresh, s_eval, s_fwd, s_bwd, s_step, s_update;
   bool phase_open = false;
   Phase cur;
@@ -246,11 +254,12 @@ static void begin_phase(b200_plan* pl) {
   pl->cur.stage_bytes = 1024;
   pl->cur.num_stages = 1;
 }
-static void end_phase(b200_plan* pl) {
+static int end_phase(b200_plan* pl) {
   Phase& p = pl->cur;
   p.num_gemm = int(pl->gj.size()) - p.first_gemm;
   p.num_ew = int(pl->ej.size()) - p.first_ew;
   p.gemm_tiles = 0;
+  p.sched_off = -1;
   int sb = 1024;
   for (int j = 0; j < p.num_gemm; ++j) {
     const GemmJob& g = pl->gj[p.first_gemm + j];
@@ -259,7 +268,45 @@ static void end_phase(b200_plan* pl) {
   }
   p.stage_bytes = sb;
   p.num_stages = std::max(1, std::min(8, mega_ring_bytes() / sb));
+  if (p.gemm_tiles > pl->sms) {
+    // longest-processing-time-first assignment of tiles to CTAs (tiles of one phase differ in weight
+    // when a wgrad slice shares the phase with dgrad tiles); ties keep index order, so CTAs working
+    // at the same time read neighbouring tiles.
+    struct T { int id; int64_t cost; };
+    std::vector<T> tiles;
+    tiles.reserve(p.gemm_tiles);
+    int id = 0;
+    for (int j = 0; j < p.num_gemm; ++j) {
+      const GemmJob& g = pl->gj[p.first_gemm + j];
+      const int num_kb = (g.K + 63) / 64;
+      const int pairs = g.a.planes == 1 ? 1 : 6;
+      for (int t = 0; t < g.num_tiles; ++t, ++id) {
+        const int ks = t / (g.m_tiles * g.n_tiles);
+        const int kb = std::min(num_kb, (ks + 1) * g.kb_per_split) - ks * g.kb_per_split;
+        tiles.push_back(T{id, int64_t(kb) * pairs * g.BN + 6 * g.BN});
+      }
+    }
+    std::stable_sort(tiles.begin(), tiles.end(), [](const T& a, const T& b) { return a.cost > b.cost; });
+    const int G = pl->sms;
+    std::vector<std::vector<int>> per(G);
+    typedef std::pair<int64_t, int> LoadCta;
+    std::priority_queue<LoadCta, std::vector<LoadCta>, std::greater<LoadCta>> pq;
+    for (int c = 0; c < G; ++c) pq.push(LoadCta(0, c));
+    for (const T& t : tiles) {
+      LoadCta lc = pq.top();
+      pq.pop();
+      per[lc.second].push_back(t.id);
+      pq.push(LoadCta(lc.first + t.cost, lc.second));
+    }
+    if (int64_t(pl->sched.size()) + G + 1 + p.gemm_tiles > kMaxSched) return fail("tile schedule table too small");
+    p.sched_off = int(pl->sched.size());
+    int off = 0;
+    for (int c = 0; c < G; ++c) { pl->sched.push_back(off); off += int(per[c].size()); }
+    pl->sched.push_back(off);
+    for (int c = 0; c < G; ++c) pl->sched.insert(pl->sched.end(), per[c].begin(), per[c].end());
+  }
   pl->ph.push_back(p);
+  return 0;
 }
 
 static Args base_args(const b200_plan* pl, int layer) {
@@ -276,7 +323,7 @@ static Args base_args(const b200_plan* pl, int layer) {
 // D[m][n] = sum_k A[m][k] B[n][k].  K-major operand: global [rows = m|n][inner = k];
 // MN-major operand (x_mn = 1): global [rows = k][inner = m|n] -- the feature-major activations.
 static int add_gemm(b200_plan* pl, const PlaneRef& A, int a_mn, const PlaneRef& Bop, int b_mn, int M, int N, int K,
-                    int BN, int epi, const Args& a) {
+                    int BN, int epi, const Args& a, int ksplit = 1) {
   if (int(pl->gj.size()) >= kMaxGemm) return fail("too many gemm jobs");
   if (b_mn && BN % 64) return fail("MN-major B operand needs a tile width that is a multiple of 64");
   GemmJob g;
@@ -287,7 +334,11 @@ static int add_gemm(b200_plan* pl, const PlaneRef& A, int a_mn, const PlaneRef& 
   g.M = M; g.N = N; g.K = K; g.BN = BN;
   g.m_tiles = (M + 127) / 128;
   g.n_tiles = (N + BN - 1) / BN;
-  g.num_tiles = g.m_tiles * g.n_tiles;
+  const int num_kb = (K + 63) / 64;
+  ksplit = std::max(1, std::min(ksplit, num_kb));
+  g.kb_per_split = (num_kb + ksplit - 1) / ksplit;
+  g.ksplit = (num_kb + g.kb_per_split - 1) / g.kb_per_split;   // no empty slices
+  g.num_tiles = g.m_tiles * g.n_tiles * g.ksplit;
   g.epi = epi;
   g.a = a;
   pl->gj.push_back(g);
@@ -305,16 +356,21 @@ static int add_ew(b200_plan* pl, int kind, const Args& a) {
 
 static Args adam_args(const b200_plan* pl) {
   Args a = base_args(pl, 0);
-  a.params = pl->d.params; a.grads = pl->d.grads; a.exp_avg = pl->d.exp_avg; a.exp_avg_sq = pl->d.exp_avg_sq;
-  a.numel = kPL.numel;
+  a.adam = pl->u.adam_tab;
   a.gnorm2 = pl->u.gnorm2;
   a.loss_acc = pl->u.loss_acc;
-  for (int l = 0; l < kNumLinear; ++l) {
-    a.w_off[l] = kPL.w[l]; a.w_rows[l] = kPL.rows[l]; a.w_cols[l] = kPL.cols[l];
-    a.w_planes[l] = pl->u.W[l];
-    a.wT_planes[l] = pl->u.WT[l];
-  }
   return a;
+}
+static AdamTab make_adam_tab(const b200_plan* pl) {
+  AdamTab t;
+  memset(&t, 0, sizeof t);
+  t.params = pl->d.params; t.grads = pl->d.grads; t.exp_avg = pl->d.exp_avg; t.exp_avg_sq = pl->d.exp_avg_sq;
+  t.numel = kPL.numel;
+  for (int l = 0; l < kNumLinear; ++l) {
+    t.w_off[l] = kPL.w[l]; t.w_rows[l] = kPL.rows[l]; t.w_cols[l] = kPL.cols[l];
+    t.w_planes[l] = pl->u.W[l];
+  }
+  return t;
 }
 
 // tile width over the batch dimension (activations are the MN-major B operand: multiples of 64)
@@ -328,6 +384,14 @@ static int tile_bn_feat(const b200_plan* pl, int n) {
   const int cap = (pl->P == 1) ? 256 : 128;
   const int r = (n + 15) & ~15;
   return std::min(cap, r);
+}
+
+// Args of the elementwise phase that follows a split-K GEMM on the small-batch path
+static void small_part_args(const b200_plan* pl, Args& a) {
+  a.out_f32 = pl->u.part;
+  a.part = pl->u.part;
+  a.ld_out = pl->u.Bs;
+  a.part_stride = int64_t(kHidden) * pl->u.Bs;
 }
 
 // forward heavy layer l (model/bilinear.py:7-13) -- train or eval flavour
@@ -349,17 +413,28 @@ static int build_fwd_layer(b200_plan* pl, int l, bool train) {
   if (l == 2) a.skip_fm = u.h_fm[0];
   if (l == 4) a.skip_fm = u.h_fm[2];
   a.out_fm = u.h_fm[l];
+  a.eval_mode = train ? 0 : 1;
   const PlaneRef& in = (l == 0) ? u.X_fm : u.h_fm[l - 1];
   const int K = kPL.cols[l];
   const int BN = tile_bn(pl, B);
-  const int epi = !train ? EPI_FWD_EVAL : (pl->large ? EPI_FWD_LARGE : EPI_FWD_SMALL);
+  if (!pl->large) {
+    small_part_args(pl, a);
+    begin_phase(pl);
+    if (add_gemm(pl, u.W[l], 0, in, 1, kHidden, B, K, BN, EPI_PARTIAL, a, kSmallSplit)) return 1;
+    a.nsplit = pl->gj.back().ksplit;
+    if (end_phase(pl)) return 1;
+    begin_phase(pl);
+    if (add_ew(pl, EW_BN_FWD_SMALL, a)) return 1;
+    if (end_phase(pl)) return 1;
+    return 0;
+  }
   begin_phase(pl);
-  if (add_gemm(pl, u.W[l], 0, in, 1, kHidden, B, K, BN, epi, a)) return 1;
-  end_phase(pl);
-  if (train && pl->large) {
+  if (add_gemm(pl, u.W[l], 0, in, 1, kHidden, B, K, BN, train ? EPI_FWD_LARGE : EPI_FWD_EVAL, a)) return 1;
+  if (end_phase(pl)) return 1;
+  if (train) {
     begin_phase(pl);
     if (add_ew(pl, EW_BN_FWD_APPLY, a)) return 1;
-    end_phase(pl);
+    if (end_phase(pl)) return 1;
   }
   return 0;
 }
@@ -372,18 +447,42 @@ static int build_decode(b200_plan* pl, bool fuse_loss) {
   a.loss_acc = u.loss_acc;
   a.grad_bias = pl->d.grads ? pl->d.grads + kPL.b[5] : nullptr;
   a.out_fm = u.dP_fm;
+  if (!pl->large) {
+    small_part_args(pl, a);
+    begin_phase(pl);
+    if (add_gemm(pl, u.W[5], 0, u.h_fm[4], 1, kDout, pl->B, kHidden, tile_bn(pl, pl->B), EPI_PARTIAL, a, kSmallSplit))
+      return 1;
+    a.nsplit = pl->gj.back().ksplit;
+    if (end_phase(pl)) return 1;
+    begin_phase(pl);
+    if (add_ew(pl, EW_DECODE_SMALL, a)) return 1;
+    if (end_phase(pl)) return 1;
+    return 0;
+  }
   begin_phase(pl);
   if (add_gemm(pl, u.W[5], 0, u.h_fm[4], 1, kDout, pl->B, kHidden, tile_bn(pl, pl->B), EPI_DECODE, a)) return 1;
-  end_phase(pl);
+  if (end_phase(pl)) return 1;
   return 0;
 }
 
+// K slices of a large-batch wgrad GEMM (K = batch): slices of about 32 k-blocks weigh as much as two
+// dgrad tiles, so the longest-first schedule balances the phase to within one such slice.
+static int wgrad_split(const b200_plan* pl) {
+  if (!pl->large) return 1;
+  const int num_kb = (pl->B + 63) / 64;
+  return std::max(1, num_kb / 32);
+}
+
 // backward phases (autograd of model/bilinear.py:31-41): for l = 4..0 { dgrad(l+1 -> l) with the
-// BN/ReLU/dropout backward of layer l in its epilogue, wgrad(l+1) } then wgrad(0).
-static int build_backward(b200_plan* pl, bool with_norm) {
+// BN/ReLU/dropout backward of layer l behind it, wgrad(l+1) } then wgrad(0).  The dgrad GEMMs read the
+// [out][in] weight planes as an MN-major A operand (no transposed copy of the weights exists).
+// `tail_ew`: elementwise job appended to the last (wgrad 0) phase, or nullptr.
+static int build_backward(b200_plan* pl, bool with_norm, const Args* tail_ew, int tail_kind) {
   const Bufs& u = pl->u;
   const b200_plan_desc& d = pl->d;
   const int B = pl->B;
+  const int wsplit = wgrad_split(pl);
+  double* wnorm = (with_norm && wsplit == 1) ? u.gnorm2 : nullptr;   // split-K: EW_SUMSQ over everything instead
   for (int l = 4; l >= 0; --l) {
     Args a = base_args(pl, l);
     a.gamma = d.params + kPL.g[l];
@@ -397,37 +496,40 @@ static int build_backward(b200_plan* pl, bool with_norm) {
     a.grad_bias = d.grads + kPL.b[l];
     a.grad_gamma = d.grads + kPL.g[l];
     a.grad_beta = d.grads + kPL.be[l];
-    a.gnorm2 = with_norm ? u.gnorm2 : nullptr;
     const int up = l + 1;                      // the Linear whose input is h_l
     const int Kd = kPL.rows[up];               // 1024, or 48 for decode
     const PlaneRef& dzu = (up == 5) ? u.dP_fm : u.dz_fm[up];
     begin_phase(pl);
-    if (add_gemm(pl, u.WT[up], 0, dzu, 1, kHidden, B, Kd, tile_bn(pl, B), pl->large ? EPI_DGRAD_LARGE : EPI_DGRAD_SMALL, a))
-      return 1;
+    if (!pl->large) {
+      small_part_args(pl, a);
+      if (add_gemm(pl, u.W[up], 1, dzu, 1, kHidden, B, Kd, tile_bn(pl, B), EPI_PARTIAL, a, kSmallSplit)) return 1;
+      a.nsplit = pl->gj.back().ksplit;
+    } else {
+      if (add_gemm(pl, u.W[up], 1, dzu, 1, kHidden, B, Kd, tile_bn(pl, B), EPI_DGRAD_LARGE, a)) return 1;
+    }
     {  // wgrad of Linear `up`: dW[out][in] = sum_b dz[b][out] h_l[b][in]
       Args w = base_args(pl, up);
       w.out_f32 = d.grads + kPL.w[up];
       w.ld_out = kHidden;
-      w.gnorm2 = with_norm ? u.gnorm2 : nullptr;
-      const PlaneRef& dzT = (up == 5) ? u.dP_fm : u.dz_fm[up];
-      if (add_gemm(pl, dzT, 0, u.h_fm[l], 0, kPL.rows[up], kHidden, B, tile_bn_feat(pl, kHidden), EPI_WGRAD, w)) return 1;
+      w.gnorm2 = wnorm;
+      if (add_gemm(pl, dzu, 0, u.h_fm[l], 0, kPL.rows[up], kHidden, B, tile_bn_feat(pl, kHidden), EPI_WGRAD, w, wsplit))
+        return 1;
     }
-    end_phase(pl);
-    if (pl->large) {
-      begin_phase(pl);
-      if (add_ew(pl, EW_BN_BWD_APPLY, a)) return 1;
-      end_phase(pl);
-    }
+    if (end_phase(pl)) return 1;
+    begin_phase(pl);
+    if (add_ew(pl, pl->large ? EW_BN_BWD_APPLY : EW_BN_BWD_SMALL, a)) return 1;
+    if (end_phase(pl)) return 1;
   }
   begin_phase(pl);
   {
     Args w = base_args(pl, 0);
     w.out_f32 = d.grads + kPL.w[0];
     w.ld_out = kDin;
-    w.gnorm2 = with_norm ? u.gnorm2 : nullptr;
-    if (add_gemm(pl, u.dz_fm[0], 0, u.X_fm, 0, kHidden, kDin, B, 32, EPI_WGRAD, w)) return 1;
+    w.gnorm2 = wnorm;
+    if (add_gemm(pl, u.dz_fm[0], 0, u.X_fm, 0, kHidden, kDin, B, 32, EPI_WGRAD, w, wsplit)) return 1;
   }
-  end_phase(pl);
+  if (tail_ew && add_ew(pl, tail_kind, *tail_ew)) return 1;
+  if (end_phase(pl)) return 1;
   return 0;
 }
 
@@ -435,10 +537,11 @@ static void zero_list_step(const b200_plan* pl, Args& a, bool fwd_acc, bool bwd_
   int k = 0;
   if (fwd_acc) { a.zero_ptr[k] = pl->u.acc_base; a.zero_bytes[k] = pl->u.acc_bytes; ++k; }
   if (bwd_grads) {
-    // gradient slots that are accumulated with atomics: decode bias always, heavy biases on the large path
-    a.zero_ptr[k] = pl->d.grads + kPL.b[5]; a.zero_bytes[k] = kDout * 4; ++k;
-    if (pl->large)
-      for (int l = 0; l < kNumHeavy; ++l) { a.zero_ptr[k] = pl->d.grads + kPL.b[l]; a.zero_bytes[k] = kHidden * 4; ++k; }
+    if (pl->large) {
+      // large batches: weight gradients are summed over K slices with reductions, heavy-layer bias
+      // gradients with atomics -> the whole flat gradient starts from zero
+      a.zero_ptr[k] = pl->d.grads; a.zero_bytes[k] = kPL.numel * 4; ++k;
+    }
   }
 }
 
@@ -451,7 +554,7 @@ static int build_plan(b200_plan* pl) {
   pl->s_refresh.first = int(pl->ph.size());
   begin_phase(pl);
   if (add_ew(pl, EW_SPLIT_W, adam_args(pl))) return 1;
-  end_phase(pl);
+  if (end_phase(pl)) return 1;
   pl->s_refresh.count = int(pl->ph.size()) - pl->s_refresh.first;
 
   // ---- eval forward (valid_bilinear.py:52)
@@ -469,7 +572,7 @@ static int build_plan(b200_plan* pl) {
     a.src = SRC_X; a.src_cols = kDin; a.out_fm = u.X_fm;
     if (add_ew(pl, EW_PREP, a)) return 1;
   }
-  end_phase(pl);
+  if (end_phase(pl)) return 1;
   for (int l = 0; l < kNumHeavy; ++l)
     if (build_fwd_layer(pl, l, false)) return 1;
   if (build_decode(pl, false)) return 1;
@@ -486,7 +589,7 @@ static int build_plan(b200_plan* pl) {
     Args b = base_args(pl, 0);
     b.keep = u.drop;
     if (add_ew(pl, EW_DROPBITS, b)) return 1;
-    end_phase(pl);
+    if (end_phase(pl)) return 1;
     return 0;
   };
 
@@ -508,16 +611,15 @@ static int build_plan(b200_plan* pl) {
     if (add_ew(pl, EW_PREP, a)) return 1;
     if (pl->large) {
       Args z = base_args(pl, 5);
-      int q = 0;
-      for (int l = 0; l < kNumHeavy; ++l) { z.zero_ptr[q] = d.grads + kPL.b[l]; z.zero_bytes[q] = kHidden * 4; ++q; }
+      zero_list_step(pl, z, false, true);
       if (add_ew(pl, EW_PREP, z)) return 1;
     }
     Args s = base_args(pl, 5);
     s.out_fm = u.dP_fm; s.grad_bias = d.grads + kPL.b[5];
     if (add_ew(pl, EW_SPLIT_DP, s)) return 1;
   }
-  end_phase(pl);
-  if (build_backward(pl, false)) return 1;
+  if (end_phase(pl)) return 1;
+  if (build_backward(pl, false, nullptr, 0)) return 1;
   pl->s_bwd.count = int(pl->ph.size()) - pl->s_bwd.first;
 
   // ---- fused step (train_bilinear.py:75-83)
@@ -526,17 +628,24 @@ static int build_plan(b200_plan* pl) {
   for (int l = 0; l < kNumHeavy; ++l)
     if (build_fwd_layer(pl, l, true)) return 1;
   if (build_decode(pl, true)) return 1;
-  if (build_backward(pl, true)) return 1;
-  begin_phase(pl);
   {
     Args a = adam_args(pl);
-    a.src_cols = 1;  // bias / BN-affine gradients only: the weight tiles were summed in the wgrad epilogues
-    if (add_ew(pl, EW_SUMSQ, a)) return 1;
+    if (wgrad_split(pl) == 1) {
+      // the weight tiles were squared in the wgrad epilogues: only bias / BN-affine gradients are left,
+      // and those were final before the last GEMM phase started
+      a.src_cols = 1;
+      if (build_backward(pl, true, &a, EW_SUMSQ)) return 1;
+    } else {
+      a.src_cols = 0;
+      if (build_backward(pl, true, nullptr, 0)) return 1;
+      begin_phase(pl);
+      if (add_ew(pl, EW_SUMSQ, a)) return 1;
+      if (end_phase(pl)) return 1;
+    }
   }
-  end_phase(pl);
   begin_phase(pl);
   if (add_ew(pl, EW_ADAM, adam_args(pl))) return 1;
-  end_phase(pl);
+  if (end_phase(pl)) return 1;
   pl->s_step.count = int(pl->ph.size()) - pl->s_step.first;
 
   // ---- optimizer alone (data parallel: after the gradient all-reduce; autograd path)
@@ -547,17 +656,22 @@ static int build_plan(b200_plan* pl) {
     a.zero_ptr[0] = u.gnorm2; a.zero_bytes[0] = 64;
     if (add_ew(pl, EW_PREP, a)) return 1;
   }
-  end_phase(pl);
+  if (end_phase(pl)) return 1;
   begin_phase(pl);
   {
     Args a = adam_args(pl);
     a.src_cols = 0;
+    a.loss_acc = nullptr;   // no forward ran in this launch: leave the caller's loss scalar alone
     if (add_ew(pl, EW_SUMSQ, a)) return 1;
   }
-  end_phase(pl);
+  if (end_phase(pl)) return 1;
   begin_phase(pl);
-  if (add_ew(pl, EW_ADAM, adam_args(pl))) return 1;
-  end_phase(pl);
+  {
+    Args a = adam_args(pl);
+    a.loss_acc = nullptr;
+    if (add_ew(pl, EW_ADAM, a)) return 1;
+  }
+  if (end_phase(pl)) return 1;
   pl->s_update.count = int(pl->ph.size()) - pl->s_update.first;
   return 0;
 }
@@ -570,6 +684,7 @@ static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, c
   p.ew_jobs = pl->u.ejobs;
   p.phases = pl->u.phases + s.first;
   p.tmaps = pl->u.tmaps;
+  p.sched = pl->u.sched;
   p.barrier = pl->u.barrier;
   p.phase_ns = pl->u.phase_ns;
   pl->last_first = s.first; pl->last_count = count;
@@ -652,6 +767,12 @@ int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
   if (e == cudaSuccess) e = cudaMemcpy(pl->u.gjobs, pl->gj.data(), pl->gj.size() * sizeof(GemmJob), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(pl->u.ejobs, pl->ej.data(), pl->ej.size() * sizeof(EwJob), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(pl->u.phases, pl->ph.data(), pl->ph.size() * sizeof(Phase), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !pl->sched.empty())
+    e = cudaMemcpy(pl->u.sched, pl->sched.data(), pl->sched.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const AdamTab tab = make_adam_tab(pl);
+    e = cudaMemcpy(pl->u.adam_tab, &tab, sizeof tab, cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) { delete pl; return fail("plan upload failed: %s", cudaGetErrorString(e)); }
   *out = pl;
   return 0;
@@ -797,11 +918,12 @@ int b200_debug_gemm(const uint16_t* a, const uint16_t* b, float* dmat, int32_t m
   g.tmap_a = 0; g.tmap_b = 1; g.a_mn = a_mn; g.b_mn = b_mn;
   g.M = m; g.N = n; g.K = k; g.BN = bn;
   g.m_tiles = (m + 127) / 128; g.n_tiles = (n + bn - 1) / bn; g.num_tiles = g.m_tiles * g.n_tiles;
+  g.ksplit = 1; g.kb_per_split = (k + 63) / 64;
   g.epi = EPI_STORE_F32;
   g.a.planes = planes; g.a.out_f32 = dmat; g.a.ld_out = n;
   Phase ph;
   memset(&ph, 0, sizeof ph);
-  ph.first_gemm = 0; ph.num_gemm = 1; ph.gemm_tiles = g.num_tiles;
+  ph.first_gemm = 0; ph.num_gemm = 1; ph.gemm_tiles = g.num_tiles; ph.sched_off = -1;
   ph.stage_bytes = planes * (128 * 128 + bn * 128);
   ph.num_stages = std::max(1, std::min(8, mega_ring_bytes() / ph.stage_bytes));
   cudaStream_t st = (cudaStream_t)stream;

@@ -10,8 +10,14 @@
 // Geometry convention for every GEMM job: D[m][n] = sum_k A[m][k] * B[n][k]
 //   m  (TMEM lane / one epilogue thread per row) = an output FEATURE,
 //   n  (TMEM column)                              = a BATCH index (fwd/dgrad) or an input feature (wgrad).
-// With features on the lanes, every BatchNorm reduction (forward mean/var, backward sum(dy),
-// sum(dy*xhat)) is a per-thread loop over TMEM columns instead of a cross-thread reduction.
+// A job may be split along K (`ksplit` slices, each slice its own tile):
+//   * small batches (the whole batch is one n tile): every fwd / dgrad GEMM is cut into 16 K slices so
+//     that ~128 SMs stream the weight matrix at once; the slices store fp32 partial sums
+//     (EPI_PARTIAL) and the following elementwise phase adds them in a fixed order while it does the
+//     BatchNorm / ReLU / dropout math with one WARP per feature (EW_BN_*_SMALL);
+//   * large batches: the wgrad GEMMs (K = batch) are cut so that their tiles weigh about as much as
+//     a few dgrad tiles; slices add into the gradient buffer with vector reductions.
+// Tiles of a phase are assigned to CTAs by a host-computed longest-first schedule (Phase::sched_off).
 #pragma once
 #include <stdint.h>
 
@@ -26,13 +32,12 @@ constexpr float kBnEps = 1e-5f;  // nn.BatchNorm1d default
 
 enum EpiKind : int32_t {
   EPI_STORE_F32 = 0,   // D -> out_f32[m][n]                       (debug / unit test)
-  EPI_FWD_SMALL = 1,   // whole batch in one tile: bias+BN(batch stats)+ReLU+dropout(+skip)
+  EPI_PARTIAL = 1,     // D -> part[ks][m][n] fp32 partial sums of K slice ks
   EPI_FWD_LARGE = 2,   // bias, write z, per-tile partial sum / sumsq -> stats
   EPI_FWD_EVAL = 3,    // scale*acc+shift, ReLU (+skip)            (BN folded, eval mode)
   EPI_DECODE = 4,      // bias -> p[b][48]; optional fused MSE loss + dP
-  EPI_DGRAD_SMALL = 5, // da (+skip grad) -> full BN backward in-tile -> dz
   EPI_DGRAD_LARGE = 6, // da (+skip grad) -> dy, partial sum(dy), sum(dy*xhat) -> stats
-  EPI_WGRAD = 7,       // dW tile -> flat grad buffer + sum of squares
+  EPI_WGRAD = 7,       // dW tile -> flat grad buffer + sum of squares (ksplit > 1: vector reductions)
 };
 
 enum EwKind : int32_t {
@@ -42,9 +47,12 @@ enum EwKind : int32_t {
   EW_BN_FWD_APPLY = 3, // large path: z -> h + keep bits + running stats
   EW_BN_BWD_APPLY = 4, // large path: dy,z -> dz + db
   EW_SPLIT_DP = 5,     // external dP [B][48] fp32 -> feature-major planes + db5 (autograd path)
-  EW_SUMSQ = 6,        // sum of squares of the flat gradient (data-parallel path, after allreduce)
+  EW_SUMSQ = 6,        // sum of squares of the flat gradient
   EW_ADAM = 7,         // clip coefficient + Adam + refresh bf16 operand planes of the weights
-  EW_SPLIT_W = 8,      // fp32 master weights -> bf16 operand planes (both layouts), no update
+  EW_SPLIT_W = 8,      // fp32 master weights -> bf16 operand planes, no update
+  EW_BN_FWD_SMALL = 9, // small path: sum K-slice partials -> bias, BN (batch or running stats), ReLU, dropout, skip
+  EW_BN_BWD_SMALL = 10,// small path: sum partials (+skip grad) -> dropout/ReLU/BN backward -> dz, dgamma, dbeta, db
+  EW_DECODE_SMALL = 11,// small path: sum partials + bias -> p; optional MSE loss, dP planes, decode bias grad
 };
 
 // bf16 "plane" tensor: value = sum_p plane[p].  planes = 1 (bf16 mode) or 3 (fp32-parity mode:
@@ -76,6 +84,20 @@ enum DynSrc : int32_t { SRC_NONE = 0, SRC_X = 1, SRC_DP = 2 };
 
 constexpr int kMaxZero = 8;
 
+// Adam / weight-plane table (one per plan, in device memory; referenced by EW_ADAM / EW_SPLIT_W /
+// EW_SUMSQ jobs through Args::adam).
+struct alignas(16) AdamTab {
+  float* params;           // flat fp32 master parameters (reference parameters() order)
+  float* grads;            // flat fp32 gradients
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+  int64_t w_off[kNumLinear];   // offsets of the six Linear weights in the flat buffer
+  int32_t w_rows[kNumLinear];
+  int32_t w_cols[kNumLinear];
+  PlaneRef w_planes[kNumLinear];   // [out][in], ld == in
+};
+
 struct alignas(16) Args {
   // ---- generic
   int32_t layer;           // 0..5
@@ -83,8 +105,12 @@ struct alignas(16) Args {
   int32_t B;               // batch rows in this launch
   int32_t fuse_loss;       // decode: 1 = fused MSE loss + dP
   // ---- fp32 outputs / inputs
-  float* out_f32;          // STORE: D; DECODE: p[b][48]; WGRAD: dW [out][in]
+  float* out_f32;          // STORE: D; PARTIAL: slice 0 of the partial sums; WGRAD: dW [out][in]
   int64_t ld_out;
+  int64_t part_stride;     // PARTIAL / EW_*_SMALL: elements between K slices
+  const float* part;       // EW_*_SMALL: partial sums [nsplit][rows][ld_out]
+  int32_t nsplit;          // EW_*_SMALL: number of K slices to add
+  int32_t eval_mode;       // EW_BN_FWD_SMALL: 1 = running statistics (folded scale/shift), no dropout
   const float* bias;       // Linear bias [M]
   const float* gamma;      // BN weight  [M]
   const float* beta;       // BN bias    [M]
@@ -123,19 +149,7 @@ struct alignas(16) Args {
   void* zero_ptr[kMaxZero];     // EW_PREP: regions to clear (16-byte multiples)
   int64_t zero_bytes[kMaxZero];
   int64_t* nbt_w[kNumHeavy];    // EW_PREP: BN counters to increment (nullptr: skip)
-  // ---- Adam
-  float* params;           // flat fp32 master parameters (reference parameters() order)
-  float* grads;            // flat fp32 gradients
-  float* exp_avg;
-  float* exp_avg_sq;
-  int64_t numel;
-  int64_t w_off[kNumLinear];   // offsets of the six Linear weights in the flat buffer
-  int32_t w_rows[kNumLinear];
-  int32_t w_cols[kNumLinear];
-  PlaneRef w_planes[kNumLinear];   // [out][in]
-  PlaneRef wT_planes[kNumLinear];  // [in][out]  (p == nullptr: not maintained)
-  int32_t adam_tile_base[kNumLinear + 1];  // prefix sums of 64x64 tiles per weight matrix (EW_ADAM)
-  int32_t pad_[1];
+  const AdamTab* adam;     // EW_ADAM / EW_SPLIT_W / EW_SUMSQ
 };
 
 struct alignas(16) GemmJob {
@@ -143,14 +157,17 @@ struct alignas(16) GemmJob {
   int32_t a_mn, b_mn;      // 1: operand is MN-major in shared memory (global layout [k][mn])
   int32_t M, N, K;
   int32_t BN;              // tile width == UMMA N (multiple of 16, <= 256)
-  int32_t m_tiles, n_tiles, num_tiles;
+  int32_t m_tiles, n_tiles, num_tiles;   // num_tiles = m_tiles * n_tiles * ksplit
+  int32_t ksplit;          // >= 1: number of K slices (tile index = (ks * n_tiles + nt) * m_tiles + mt)
+  int32_t kb_per_split;    // 64-element k-blocks per slice
   int32_t epi;
+  int32_t pad_[3];
   Args a;
 };
 
 struct alignas(16) EwJob {
   int32_t kind;
-  int32_t pad;
+  int32_t pad[3];
   Args a;
 };
 
@@ -159,7 +176,8 @@ struct Phase {
   int32_t first_ew, num_ew;
   int32_t stage_bytes;      // smem ring geometry of this phase (max over its GEMM jobs)
   int32_t num_stages;
-  int32_t pad;
+  int32_t sched_off;        // < 0: tiles are strided over CTAs; else offset into MegaParams::sched of
+                            // [grid + 1 begin offsets][tile ids ...] (longest-first per CTA)
 };
 
 struct MegaParams {
@@ -167,8 +185,9 @@ struct MegaParams {
   const EwJob* ew_jobs;
   const Phase* phases;
   const void* tmaps;        // array of CUtensorMap (128 B each, 64 B aligned)
+  const int32_t* sched;     // per-phase tile schedules (see Phase::sched_off)
   unsigned int* barrier;    // grid barrier counter (zeroed before launch)
-  unsigned long long* phase_ns;  // [num_phases + 1] globaltimer stamps written by block 0 (nullptr: off)
+  unsigned long long* phase_ns;  // [8 * (num_phases + 1)] globaltimer stamps written by block 0 (nullptr: off)
   int32_t num_phases;
   int32_t pad;
   Dyn dyn;
