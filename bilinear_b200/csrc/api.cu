@@ -127,15 +127,17 @@ struct Carver {
   template <class T> T* take_n(int64_t n) { return reinterpret_cast<T*>(take(n * int64_t(sizeof(T)))); }
 };
 
-constexpr int kMaxTmaps = 128, kMaxGemm = 64, kMaxEw = 96, kMaxPhases = 160;
+constexpr int kMaxTmaps = 128, kMaxPhases = 160, kMaxCtas = 192;
 constexpr int kMaxSched = 1 << 18;   // int32 entries of per-phase tile schedules
 constexpr int kSmallSplit = 16;      // K slices of the small-batch GEMMs (K = 1024 -> one k-block each)
 
 struct Bufs {
-  CUtensorMap* tmaps; GemmJob* gjobs; EwJob* ejobs; Phase* phases; unsigned int* barrier;
+  CUtensorMap* tmaps; PhaseBlob* blobs; CtaTiles* cta_tiles; unsigned int* barrier;
   unsigned long long* phase_ns;
-  int32_t* sched; AdamTab* adam_tab;
+  int32_t* sched; AdamTab* adam_tab; FoldTab* fold_tab;
+  uint16_t* wplanes; int64_t wplane_stride;   // bf16 planes of the whole flat parameter buffer
   float* part;                       // small path: [kSmallSplit][1024][Bs] fp32 partial sums
+  float* x_save;                     // small path: copy of the input batch [Bs][32] fp32
   uint8_t* acc_base; int64_t acc_bytes;
   double* loss_acc; double* gnorm2; double* stats_f[kNumHeavy]; double* stats_b[kNumHeavy];
   float* save_mean[kNumHeavy]; float* save_rstd[kNumHeavy]; float* scale[kNumHeavy]; float* shift[kNumHeavy];
@@ -165,14 +167,15 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
   const int64_t ldw = Bs / 32;
   u.Bs = Bs; u.ldw = ldw;
   u.tmaps = c.take_n<CUtensorMap>(kMaxTmaps);
-  u.gjobs = c.take_n<GemmJob>(kMaxGemm);
-  u.ejobs = c.take_n<EwJob>(kMaxEw);
-  u.phases = c.take_n<Phase>(kMaxPhases);
+  u.blobs = c.take_n<PhaseBlob>(kMaxPhases);
+  u.cta_tiles = c.take_n<CtaTiles>(int64_t(kMaxPhases) * kMaxCtas);
   u.barrier = c.take_n<unsigned int>(64);
   u.phase_ns = c.take_n<unsigned long long>(8 * (kMaxPhases + 1));
   u.sched = c.take_n<int32_t>(kMaxSched);
   u.adam_tab = c.take_n<AdamTab>(1);
+  u.fold_tab = c.take_n<FoldTab>(1);
   u.part = large ? nullptr : c.take_n<float>(int64_t(kSmallSplit) * kHidden * Bs);
+  u.x_save = large ? nullptr : c.take_n<float>(Bs * kDin);
   // accumulators cleared at the start of every step (one contiguous region)
   const int64_t acc0 = (c.off + 1023) & ~int64_t(1023);
   u.loss_acc = c.take_n<double>(16);
@@ -186,8 +189,14 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
     u.save_mean[l] = c.take_n<float>(kHidden); u.save_rstd[l] = c.take_n<float>(kHidden);
     u.scale[l] = c.take_n<float>(kHidden); u.shift[l] = c.take_n<float>(kHidden);
   }
+  // operand planes of the weights: ONE bf16 image of the flat parameter buffer per plane, so the Adam
+  // phase writes them at the index it is already at; each weight matrix is TMA-mapped where it lies
+  u.wplane_stride = (kPL.numel + 511) & ~int64_t(511);
+  u.wplanes = c.take_n<uint16_t>(u.wplane_stride * P);
   for (int l = 0; l < kNumLinear; ++l) {
-    u.W[l] = take_planes(c, P, kPL.rows[l], kPL.cols[l]);
+    u.W[l].p = u.wplanes ? u.wplanes + kPL.w[l] : nullptr;
+    u.W[l].plane_stride = u.wplane_stride;
+    u.W[l].ld = kPL.cols[l];
   }
   u.X_fm = take_planes(c, P, kDin, Bs);
   const int64_t zbytes = int64_t(kHidden) * Bs * (P == 1 ? 2 : 4);
@@ -228,13 +237,11 @@ struct b200_plan {
   bool large;
   int sms;
   std::vector<CUtensorMap> tm;
-  std::vector<GemmJob> gj;
-  std::vector<EwJob> ej;
-  std::vector<Phase> ph;
+  std::vector<PhaseBlob> blobs;
+  std::vector<CtaTiles> cta_tiles;   // [phase][sms]
   std::vector<int32_t> sched;
   Sched s_refresh, s_eval, s_fwd, s_bwd, s_step, s_update;
-  bool phase_open = false;
-  Phase cur;
+  PhaseBlob cur;
   int last_first = 0, last_count = 0;
 };
 
@@ -248,27 +255,26 @@ static int add_map(b200_plan* pl, const PlaneRef& r, int64_t inner, int64_t rows
 }
 
 static void begin_phase(b200_plan* pl) {
-  pl->cur = Phase{};
-  pl->cur.first_gemm = int(pl->gj.size());
-  pl->cur.first_ew = int(pl->ej.size());
-  pl->cur.stage_bytes = 1024;
-  pl->cur.num_stages = 1;
+  memset(&pl->cur, 0, sizeof pl->cur);
+  pl->cur.ph.stage_bytes = 1024;
+  pl->cur.ph.num_stages = 1;
+  pl->cur.ph.sched_off = -1;
 }
 static int end_phase(b200_plan* pl) {
-  Phase& p = pl->cur;
-  p.num_gemm = int(pl->gj.size()) - p.first_gemm;
-  p.num_ew = int(pl->ej.size()) - p.first_ew;
+  Phase& p = pl->cur.ph;
   p.gemm_tiles = 0;
-  p.sched_off = -1;
   int sb = 1024;
   for (int j = 0; j < p.num_gemm; ++j) {
-    const GemmJob& g = pl->gj[p.first_gemm + j];
+    const GemmJob& g = pl->cur.gj[j];
     p.gemm_tiles += g.num_tiles;
     sb = std::max(sb, g.a.planes * (128 * 128 + g.BN * 128));
   }
   p.stage_bytes = sb;
   p.num_stages = std::max(1, std::min(8, mega_ring_bytes() / sb));
-  if (p.gemm_tiles > pl->sms) {
+  const int G = pl->sms;
+  std::vector<CtaTiles> ct(G);
+  for (int c = 0; c < G; ++c) memset(&ct[c], 0, sizeof(CtaTiles));
+  if (p.gemm_tiles > 0) {
     // longest-processing-time-first assignment of tiles to CTAs (tiles of one phase differ in weight
     // when a wgrad slice shares the phase with dgrad tiles); ties keep index order, so CTAs working
     // at the same time read neighbouring tiles.
@@ -277,7 +283,7 @@ static int end_phase(b200_plan* pl) {
     tiles.reserve(p.gemm_tiles);
     int id = 0;
     for (int j = 0; j < p.num_gemm; ++j) {
-      const GemmJob& g = pl->gj[p.first_gemm + j];
+      const GemmJob& g = pl->cur.gj[j];
       const int num_kb = (g.K + 63) / 64;
       const int pairs = g.a.planes == 1 ? 1 : 6;
       for (int t = 0; t < g.num_tiles; ++t, ++id) {
@@ -287,7 +293,6 @@ static int end_phase(b200_plan* pl) {
       }
     }
     std::stable_sort(tiles.begin(), tiles.end(), [](const T& a, const T& b) { return a.cost > b.cost; });
-    const int G = pl->sms;
     std::vector<std::vector<int>> per(G);
     typedef std::pair<int64_t, int> LoadCta;
     std::priority_queue<LoadCta, std::vector<LoadCta>, std::greater<LoadCta>> pq;
@@ -298,14 +303,20 @@ static int end_phase(b200_plan* pl) {
       per[lc.second].push_back(t.id);
       pq.push(LoadCta(lc.first + t.cost, lc.second));
     }
-    if (int64_t(pl->sched.size()) + G + 1 + p.gemm_tiles > kMaxSched) return fail("tile schedule table too small");
+    if (int64_t(pl->sched.size()) + p.gemm_tiles > kMaxSched) return fail("tile schedule table too small");
     p.sched_off = int(pl->sched.size());
     int off = 0;
-    for (int c = 0; c < G; ++c) { pl->sched.push_back(off); off += int(per[c].size()); }
-    pl->sched.push_back(off);
-    for (int c = 0; c < G; ++c) pl->sched.insert(pl->sched.end(), per[c].begin(), per[c].end());
+    for (int c = 0; c < G; ++c) {
+      ct[c].begin = off;
+      off += int(per[c].size());
+      ct[c].end = off;
+      for (int i = 0; i < kTileSlots && i < int(per[c].size()); ++i) ct[c].tile[i] = per[c][i];
+      pl->sched.insert(pl->sched.end(), per[c].begin(), per[c].end());
+    }
   }
-  pl->ph.push_back(p);
+  if (int(pl->blobs.size()) >= kMaxPhases) return fail("too many phases");
+  pl->blobs.push_back(pl->cur);
+  pl->cta_tiles.insert(pl->cta_tiles.end(), ct.begin(), ct.end());
   return 0;
 }
 
@@ -324,7 +335,7 @@ static Args base_args(const b200_plan* pl, int layer) {
 // MN-major operand (x_mn = 1): global [rows = k][inner = m|n] -- the feature-major activations.
 static int add_gemm(b200_plan* pl, const PlaneRef& A, int a_mn, const PlaneRef& Bop, int b_mn, int M, int N, int K,
                     int BN, int epi, const Args& a, int ksplit = 1) {
-  if (int(pl->gj.size()) >= kMaxGemm) return fail("too many gemm jobs");
+  if (pl->cur.ph.num_gemm >= kBlobGemm) return fail("too many gemm jobs in one phase");
   if (b_mn && BN % 64) return fail("MN-major B operand needs a tile width that is a multiple of 64");
   GemmJob g;
   memset(&g, 0, sizeof g);
@@ -341,16 +352,17 @@ static int add_gemm(b200_plan* pl, const PlaneRef& A, int a_mn, const PlaneRef& 
   g.num_tiles = g.m_tiles * g.n_tiles * g.ksplit;
   g.epi = epi;
   g.a = a;
-  pl->gj.push_back(g);
+  pl->cur.gj[pl->cur.ph.num_gemm++] = g;
   return 0;
 }
+static const GemmJob& last_gemm(const b200_plan* pl) { return pl->cur.gj[pl->cur.ph.num_gemm - 1]; }
 static int add_ew(b200_plan* pl, int kind, const Args& a) {
-  if (int(pl->ej.size()) >= kMaxEw) return fail("too many elementwise jobs");
+  if (pl->cur.ph.num_ew >= kBlobEw) return fail("too many elementwise jobs in one phase");
   EwJob e;
   memset(&e, 0, sizeof e);
   e.kind = kind;
   e.a = a;
-  pl->ej.push_back(e);
+  pl->cur.ej[pl->cur.ph.num_ew++] = e;
   return 0;
 }
 
@@ -366,9 +378,18 @@ static AdamTab make_adam_tab(const b200_plan* pl) {
   memset(&t, 0, sizeof t);
   t.params = pl->d.params; t.grads = pl->d.grads; t.exp_avg = pl->d.exp_avg; t.exp_avg_sq = pl->d.exp_avg_sq;
   t.numel = kPL.numel;
-  for (int l = 0; l < kNumLinear; ++l) {
-    t.w_off[l] = kPL.w[l]; t.w_rows[l] = kPL.rows[l]; t.w_cols[l] = kPL.cols[l];
-    t.w_planes[l] = pl->u.W[l];
+  for (int l = 0; l < kNumLinear; ++l) { t.w_off[l] = kPL.w[l]; t.w_rows[l] = kPL.rows[l]; t.w_cols[l] = kPL.cols[l]; }
+  t.planes = pl->u.wplanes;
+  t.plane_stride = pl->u.wplane_stride;
+  return t;
+}
+static FoldTab make_fold_tab(const b200_plan* pl) {
+  FoldTab t;
+  memset(&t, 0, sizeof t);
+  for (int l = 0; l < kNumHeavy; ++l) {
+    t.bias[l] = pl->d.params + kPL.b[l]; t.gamma[l] = pl->d.params + kPL.g[l]; t.beta[l] = pl->d.params + kPL.be[l];
+    t.run_mean[l] = pl->d.running_mean[l]; t.run_var[l] = pl->d.running_var[l];
+    t.scale[l] = pl->u.scale[l]; t.shift[l] = pl->u.shift[l];
   }
   return t;
 }
@@ -395,7 +416,7 @@ static void small_part_args(const b200_plan* pl, Args& a) {
 }
 
 // forward heavy layer l (model/bilinear.py:7-13) -- train or eval flavour
-static int build_fwd_layer(b200_plan* pl, int l, bool train) {
+static int build_fwd_layer(b200_plan* pl, int l, bool train, bool phase_open = false) {
   const Bufs& u = pl->u;
   const b200_plan_desc& d = pl->d;
   const int B = pl->B;
@@ -419,9 +440,21 @@ static int build_fwd_layer(b200_plan* pl, int l, bool train) {
   const int BN = tile_bn(pl, B);
   if (!pl->large) {
     small_part_args(pl, a);
+    a.drop = nullptr;   // dropout bits are drawn inline (drop_word)
+    if (l == 0) {
+      // the 32-wide first Linear runs on the CUDA cores inside the elementwise job; it joins the phase
+      // the caller has open (accumulator clearing), so the forward pass starts with ONE phase
+      a.part = nullptr; a.nsplit = 0;
+      a.w_src = d.params + kPL.w[0];
+      a.x_save = train ? u.x_save : nullptr;
+      if (!phase_open) begin_phase(pl);
+      if (add_ew(pl, EW_BN_FWD_SMALL, a)) return 1;
+      if (end_phase(pl)) return 1;
+      return 0;
+    }
     begin_phase(pl);
     if (add_gemm(pl, u.W[l], 0, in, 1, kHidden, B, K, BN, EPI_PARTIAL, a, kSmallSplit)) return 1;
-    a.nsplit = pl->gj.back().ksplit;
+    a.nsplit = last_gemm(pl).ksplit;
     if (end_phase(pl)) return 1;
     begin_phase(pl);
     if (add_ew(pl, EW_BN_FWD_SMALL, a)) return 1;
@@ -439,7 +472,7 @@ static int build_fwd_layer(b200_plan* pl, int l, bool train) {
   return 0;
 }
 
-static int build_decode(b200_plan* pl, bool fuse_loss) {
+static int build_decode(b200_plan* pl, bool fuse_loss, bool train) {
   const Bufs& u = pl->u;
   Args a = base_args(pl, 5);
   a.bias = pl->d.params + kPL.b[5];
@@ -449,10 +482,13 @@ static int build_decode(b200_plan* pl, bool fuse_loss) {
   a.out_fm = u.dP_fm;
   if (!pl->large) {
     small_part_args(pl, a);
+    if (train)
+      for (int l = 0; l < kNumHeavy; ++l) a.nbt_w[l] = pl->d.num_batches_tracked[l];
+    if (fuse_loss) a.gnorm2 = u.gnorm2;
     begin_phase(pl);
     if (add_gemm(pl, u.W[5], 0, u.h_fm[4], 1, kDout, pl->B, kHidden, tile_bn(pl, pl->B), EPI_PARTIAL, a, kSmallSplit))
       return 1;
-    a.nsplit = pl->gj.back().ksplit;
+    a.nsplit = last_gemm(pl).ksplit;
     if (end_phase(pl)) return 1;
     begin_phase(pl);
     if (add_ew(pl, EW_DECODE_SMALL, a)) return 1;
@@ -503,7 +539,16 @@ static int build_backward(b200_plan* pl, bool with_norm, const Args* tail_ew, in
     if (!pl->large) {
       small_part_args(pl, a);
       if (add_gemm(pl, u.W[up], 1, dzu, 1, kHidden, B, Kd, tile_bn(pl, B), EPI_PARTIAL, a, kSmallSplit)) return 1;
-      a.nsplit = pl->gj.back().ksplit;
+      a.nsplit = last_gemm(pl).ksplit;
+      a.gnorm2 = with_norm ? u.gnorm2 : nullptr;   // bias / BatchNorm-affine squares are added by the job itself
+      if (l == 0) {
+        // first layer: dW0 = dz0^T x is taken inside the elementwise job (K = 32), which also ends the
+        // backward pass -> it publishes the loss when the optimizer phase does not follow
+        a.grad_w0 = d.grads + kPL.w[0];
+        a.x_save = u.x_save;
+        a.out_fm = PlaneRef{nullptr, 0, 0};
+        a.loss_acc = with_norm ? u.loss_acc : nullptr;
+      }
     } else {
       if (add_gemm(pl, u.W[up], 1, dzu, 1, kHidden, B, Kd, tile_bn(pl, B), EPI_DGRAD_LARGE, a)) return 1;
     }
@@ -520,6 +565,7 @@ static int build_backward(b200_plan* pl, bool with_norm, const Args* tail_ew, in
     if (add_ew(pl, pl->large ? EW_BN_BWD_APPLY : EW_BN_BWD_SMALL, a)) return 1;
     if (end_phase(pl)) return 1;
   }
+  if (!pl->large) return 0;
   begin_phase(pl);
   {
     Args w = base_args(pl, 0);
@@ -551,58 +597,65 @@ static int build_plan(b200_plan* pl) {
   const bool train = pl->kind == B200_PLAN_TRAIN;
 
   // ---- refresh: master weights -> operand planes
-  pl->s_refresh.first = int(pl->ph.size());
+  pl->s_refresh.first = int(pl->blobs.size());
   begin_phase(pl);
   if (add_ew(pl, EW_SPLIT_W, adam_args(pl))) return 1;
   if (end_phase(pl)) return 1;
-  pl->s_refresh.count = int(pl->ph.size()) - pl->s_refresh.first;
+  pl->s_refresh.count = int(pl->blobs.size()) - pl->s_refresh.first;
 
   // ---- eval forward (valid_bilinear.py:52)
-  pl->s_eval.first = int(pl->ph.size());
-  begin_phase(pl);
-  for (int l = 0; l < kNumHeavy; ++l) {
-    Args a = base_args(pl, l);
-    a.bias = d.params + kPL.b[l]; a.gamma = d.params + kPL.g[l]; a.beta = d.params + kPL.be[l];
-    a.run_mean = d.running_mean[l]; a.run_var = d.running_var[l];
-    a.scale_w = u.scale[l]; a.shift_w = u.shift[l];
-    if (add_ew(pl, EW_BN_FOLD, a)) return 1;
+  pl->s_eval.first = int(pl->blobs.size());
+  if (pl->large) {
+    begin_phase(pl);
+    {
+      Args a = base_args(pl, 0);
+      a.fold = u.fold_tab;
+      if (add_ew(pl, EW_BN_FOLD, a)) return 1;
+    }
+    {
+      Args a = base_args(pl, 0);
+      a.src = SRC_X; a.src_cols = kDin; a.out_fm = u.X_fm;
+      if (add_ew(pl, EW_PREP, a)) return 1;
+    }
+    if (end_phase(pl)) return 1;
   }
-  {
-    Args a = base_args(pl, 0);
-    a.src = SRC_X; a.src_cols = kDin; a.out_fm = u.X_fm;
-    if (add_ew(pl, EW_PREP, a)) return 1;
-  }
-  if (end_phase(pl)) return 1;
   for (int l = 0; l < kNumHeavy; ++l)
     if (build_fwd_layer(pl, l, false)) return 1;
-  if (build_decode(pl, false)) return 1;
-  pl->s_eval.count = int(pl->ph.size()) - pl->s_eval.first;
+  if (build_decode(pl, false, false)) return 1;
+  pl->s_eval.count = int(pl->blobs.size()) - pl->s_eval.first;
   if (!train) return 0;
 
+  // first phase of a training-mode forward: clear the accumulators; large batches also split x into
+  // operand planes, draw the dropout bits and bump the BatchNorm counters here (the small path does
+  // those inline / at the end of the forward).  The small path leaves the phase OPEN for layer 0.
   auto prep_fwd = [&](bool zero_grads) -> int {
     begin_phase(pl);
     Args a = base_args(pl, 0);
-    a.src = SRC_X; a.src_cols = kDin; a.out_fm = u.X_fm;
     zero_list_step(pl, a, true, zero_grads);
-    for (int l = 0; l < kNumHeavy; ++l) a.nbt_w[l] = d.num_batches_tracked[l];
+    if (pl->large) {
+      a.src = SRC_X; a.src_cols = kDin; a.out_fm = u.X_fm;
+      for (int l = 0; l < kNumHeavy; ++l) a.nbt_w[l] = d.num_batches_tracked[l];
+    }
     if (add_ew(pl, EW_PREP, a)) return 1;
-    Args b = base_args(pl, 0);
-    b.keep = u.drop;
-    if (add_ew(pl, EW_DROPBITS, b)) return 1;
-    if (end_phase(pl)) return 1;
+    if (pl->large) {
+      Args b = base_args(pl, 0);
+      b.keep = u.drop;
+      if (add_ew(pl, EW_DROPBITS, b)) return 1;
+      if (end_phase(pl)) return 1;
+    }
     return 0;
   };
 
   // ---- training-mode forward alone (autograd path)
-  pl->s_fwd.first = int(pl->ph.size());
+  pl->s_fwd.first = int(pl->blobs.size());
   if (prep_fwd(false)) return 1;
   for (int l = 0; l < kNumHeavy; ++l)
-    if (build_fwd_layer(pl, l, true)) return 1;
-  if (build_decode(pl, false)) return 1;
-  pl->s_fwd.count = int(pl->ph.size()) - pl->s_fwd.first;
+    if (build_fwd_layer(pl, l, true, l == 0 && !pl->large)) return 1;
+  if (build_decode(pl, false, true)) return 1;
+  pl->s_fwd.count = int(pl->blobs.size()) - pl->s_fwd.first;
 
   // ---- backward alone (autograd path): dP comes from the caller
-  pl->s_bwd.first = int(pl->ph.size());
+  pl->s_bwd.first = int(pl->blobs.size());
   begin_phase(pl);
   {
     Args a = base_args(pl, 5);
@@ -620,15 +673,17 @@ static int build_plan(b200_plan* pl) {
   }
   if (end_phase(pl)) return 1;
   if (build_backward(pl, false, nullptr, 0)) return 1;
-  pl->s_bwd.count = int(pl->ph.size()) - pl->s_bwd.first;
+  pl->s_bwd.count = int(pl->blobs.size()) - pl->s_bwd.first;
 
   // ---- fused step (train_bilinear.py:75-83)
-  pl->s_step.first = int(pl->ph.size());
+  pl->s_step.first = int(pl->blobs.size());
   if (prep_fwd(true)) return 1;
   for (int l = 0; l < kNumHeavy; ++l)
-    if (build_fwd_layer(pl, l, true)) return 1;
-  if (build_decode(pl, true)) return 1;
-  {
+    if (build_fwd_layer(pl, l, true, l == 0 && !pl->large)) return 1;
+  if (build_decode(pl, true, true)) return 1;
+  if (!pl->large) {
+    if (build_backward(pl, true, nullptr, 0)) return 1;
+  } else {
     Args a = adam_args(pl);
     if (wgrad_split(pl) == 1) {
       // the weight tiles were squared in the wgrad epilogues: only bias / BN-affine gradients are left,
@@ -646,10 +701,10 @@ static int build_plan(b200_plan* pl) {
   begin_phase(pl);
   if (add_ew(pl, EW_ADAM, adam_args(pl))) return 1;
   if (end_phase(pl)) return 1;
-  pl->s_step.count = int(pl->ph.size()) - pl->s_step.first;
+  pl->s_step.count = int(pl->blobs.size()) - pl->s_step.first;
 
   // ---- optimizer alone (data parallel: after the gradient all-reduce; autograd path)
-  pl->s_update.first = int(pl->ph.size());
+  pl->s_update.first = int(pl->blobs.size());
   begin_phase(pl);
   {
     Args a = base_args(pl, 0);
@@ -672,7 +727,7 @@ static int build_plan(b200_plan* pl) {
     if (add_ew(pl, EW_ADAM, a)) return 1;
   }
   if (end_phase(pl)) return 1;
-  pl->s_update.count = int(pl->ph.size()) - pl->s_update.first;
+  pl->s_update.count = int(pl->blobs.size()) - pl->s_update.first;
   return 0;
 }
 
@@ -680,9 +735,8 @@ static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, c
   if (count <= 0) return fail("empty schedule (plan kind does not support this call)");
   MegaParams p;
   memset(&p, 0, sizeof p);
-  p.gemm_jobs = pl->u.gjobs;
-  p.ew_jobs = pl->u.ejobs;
-  p.phases = pl->u.phases + s.first;
+  p.blobs = pl->u.blobs + s.first;
+  p.cta_tiles = pl->u.cta_tiles + size_t(s.first) * pl->sms;
   p.tmaps = pl->u.tmaps;
   p.sched = pl->u.sched;
   p.barrier = pl->u.barrier;
@@ -764,14 +818,18 @@ int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
   // schedules + tensor maps -> device (pageable host memory: cudaMemcpy is synchronous, done once)
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = cudaMemcpy(pl->u.tmaps, pl->tm.data(), pl->tm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(pl->u.gjobs, pl->gj.data(), pl->gj.size() * sizeof(GemmJob), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(pl->u.ejobs, pl->ej.data(), pl->ej.size() * sizeof(EwJob), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(pl->u.phases, pl->ph.data(), pl->ph.size() * sizeof(Phase), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->u.blobs, pl->blobs.data(), pl->blobs.size() * sizeof(PhaseBlob), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(pl->u.cta_tiles, pl->cta_tiles.data(), pl->cta_tiles.size() * sizeof(CtaTiles), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && !pl->sched.empty())
     e = cudaMemcpy(pl->u.sched, pl->sched.data(), pl->sched.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     const AdamTab tab = make_adam_tab(pl);
     e = cudaMemcpy(pl->u.adam_tab, &tab, sizeof tab, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) {
+    const FoldTab tab = make_fold_tab(pl);
+    e = cudaMemcpy(pl->u.fold_tab, &tab, sizeof tab, cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) { delete pl; return fail("plan upload failed: %s", cudaGetErrorString(e)); }
   *out = pl;
@@ -892,9 +950,10 @@ int b200_debug_phase_ns(b200_plan* plan, int64_t* ns_out, int32_t* kinds_out, in
     // producer done, MMA issue done, first accumulator ready, epilogue done, work done (block 0), spare
     ns_out[8 * i] = int64_t(t[8 * (i + 1)] - t[8 * i]);
     for (int k = 1; k < 8; ++k) ns_out[8 * i + k] = t[8 * i + k] >= t[8 * i] ? int64_t(t[8 * i + k] - t[8 * i]) : -1;
-    const Phase& ph = plan->ph[plan->last_first + i];
-    if (kinds_out) kinds_out[i] = ph.gemm_tiles > 0 ? 0 : 1 + plan->ej[ph.first_ew].kind;
-    if (tiles_out) tiles_out[i] = ph.gemm_tiles > 0 ? (ph.gemm_tiles | (plan->gj[ph.first_gemm].epi << 24)) : ph.num_ew;
+    const PhaseBlob& bl = plan->blobs[plan->last_first + i];
+    const Phase& ph = bl.ph;
+    if (kinds_out) kinds_out[i] = ph.gemm_tiles > 0 ? 0 : 1 + bl.ej[0].kind;
+    if (tiles_out) tiles_out[i] = ph.gemm_tiles > 0 ? (ph.gemm_tiles | (bl.gj[0].epi << 24)) : ph.num_ew;
   }
   *count_out = n;
   return 0;
@@ -921,20 +980,20 @@ int b200_debug_gemm(const uint16_t* a, const uint16_t* b, float* dmat, int32_t m
   g.ksplit = 1; g.kb_per_split = (k + 63) / 64;
   g.epi = EPI_STORE_F32;
   g.a.planes = planes; g.a.out_f32 = dmat; g.a.ld_out = n;
-  Phase ph;
-  memset(&ph, 0, sizeof ph);
-  ph.first_gemm = 0; ph.num_gemm = 1; ph.gemm_tiles = g.num_tiles; ph.sched_off = -1;
-  ph.stage_bytes = planes * (128 * 128 + bn * 128);
-  ph.num_stages = std::max(1, std::min(8, mega_ring_bytes() / ph.stage_bytes));
+  static PhaseBlob blob;   // host staging (one debug call at a time)
+  memset(&blob, 0, sizeof blob);
+  blob.ph.num_gemm = 1; blob.ph.gemm_tiles = g.num_tiles; blob.ph.sched_off = -1;
+  blob.ph.stage_bytes = planes * (128 * 128 + bn * 128);
+  blob.ph.num_stages = std::max(1, std::min(8, mega_ring_bytes() / blob.ph.stage_bytes));
+  blob.gj[0] = g;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemcpyAsync(s, tm, sizeof tm, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(s + 1024, &g, sizeof g, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(s + 1024 + 4096, &ph, sizeof ph, cudaMemcpyHostToDevice, st));
-  CK(cudaStreamSynchronize(st));  // the host staging copies above live on this stack frame
+  CK(cudaMemcpyAsync(s + 1024, &blob, sizeof blob, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // the host staging copies above must be consumed before we return
   MegaParams p;
   memset(&p, 0, sizeof p);
-  p.tmaps = s; p.gemm_jobs = reinterpret_cast<GemmJob*>(s + 1024); p.phases = reinterpret_cast<Phase*>(s + 1024 + 4096);
-  p.ew_jobs = nullptr; p.barrier = reinterpret_cast<unsigned int*>(s + 1024 + 8192); p.num_phases = 1;
+  p.tmaps = s; p.blobs = reinterpret_cast<PhaseBlob*>(s + 1024);
+  p.barrier = reinterpret_cast<unsigned int*>(s + 32768); p.num_phases = 1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

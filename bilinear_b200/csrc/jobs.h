@@ -43,7 +43,7 @@ enum EpiKind : int32_t {
 enum EwKind : int32_t {
   EW_PREP = 0,         // zero accumulators, split x into feature-major planes, bump BN counters
   EW_DROPBITS = 1,     // pack injected uint8 masks / generate Philox bits -> [f][b/32] words
-  EW_BN_FOLD = 2,      // eval: scale = g*rsqrt(rv+eps), shift = b + (bias-rm)*scale
+  EW_BN_FOLD = 2,      // eval: scale = g*rsqrt(rv+eps), shift = b + (bias-rm)*scale, all five layers (Args::fold)
   EW_BN_FWD_APPLY = 3, // large path: z -> h + keep bits + running stats
   EW_BN_BWD_APPLY = 4, // large path: dy,z -> dz + db
   EW_SPLIT_DP = 5,     // external dP [B][48] fp32 -> feature-major planes + db5 (autograd path)
@@ -84,6 +84,17 @@ enum DynSrc : int32_t { SRC_NONE = 0, SRC_X = 1, SRC_DP = 2 };
 
 constexpr int kMaxZero = 8;
 
+// BatchNorm folding table for eval mode (one per plan, in device memory; EW_BN_FOLD via Args::fold).
+struct alignas(16) FoldTab {
+  const float* bias[kNumHeavy];
+  const float* gamma[kNumHeavy];
+  const float* beta[kNumHeavy];
+  const float* run_mean[kNumHeavy];
+  const float* run_var[kNumHeavy];
+  float* scale[kNumHeavy];
+  float* shift[kNumHeavy];
+};
+
 // Adam / weight-plane table (one per plan, in device memory; referenced by EW_ADAM / EW_SPLIT_W /
 // EW_SUMSQ jobs through Args::adam).
 struct alignas(16) AdamTab {
@@ -95,7 +106,8 @@ struct alignas(16) AdamTab {
   int64_t w_off[kNumLinear];   // offsets of the six Linear weights in the flat buffer
   int32_t w_rows[kNumLinear];
   int32_t w_cols[kNumLinear];
-  PlaneRef w_planes[kNumLinear];   // [out][in], ld == in
+  uint16_t* planes;        // bf16 operand planes of the WHOLE flat buffer: plane q of parameter e lives at
+  int64_t plane_stride;    // planes[q * plane_stride + e]; the weight matrices are TMA-mapped in place
 };
 
 struct alignas(16) Args {
@@ -122,8 +134,6 @@ struct alignas(16) Args {
   double* stats;           // [M][2] accumulators (large path fwd: sum z, sum z^2; bwd: sum dy, sum dy*xhat)
   const float* scale;      // eval: folded BN scale [M]
   const float* shift;      // eval: folded BN shift [M]
-  float* scale_w;          // EW_BN_FOLD outputs
-  float* shift_w;
   // ---- feature-major scratch ([f][ldT])
   void* zT;                // pre-BN activations, fp32 (planes==3) or bf16 (planes==1)
   void* dyT;               // large path: masked upstream grad, same dtype rule as zT
@@ -148,8 +158,12 @@ struct alignas(16) Args {
   int32_t src_cols;        // EW_PREP: columns of the source; EW_SUMSQ: 1 = non-weight tensors only
   void* zero_ptr[kMaxZero];     // EW_PREP: regions to clear (16-byte multiples)
   int64_t zero_bytes[kMaxZero];
-  int64_t* nbt_w[kNumHeavy];    // EW_PREP: BN counters to increment (nullptr: skip)
+  int64_t* nbt_w[kNumHeavy];    // EW_PREP / EW_DECODE_SMALL: BN counters to increment (nullptr: skip)
+  const float* w_src;      // EW_BN_FWD_SMALL without partials: fp32 master weight [1024][32] of the first Linear
+  float* x_save;           // small path: copy of x [B][32] kept by the forward for the fused first-layer wgrad
+  float* grad_w0;          // EW_BN_BWD_SMALL of the first layer: dW0 [1024][32] (nullptr: no fused wgrad)
   const AdamTab* adam;     // EW_ADAM / EW_SPLIT_W / EW_SUMSQ
+  const FoldTab* fold;     // EW_BN_FOLD
 };
 
 struct alignas(16) GemmJob {
@@ -172,20 +186,39 @@ struct alignas(16) EwJob {
 };
 
 struct Phase {
-  int32_t first_gemm, num_gemm, gemm_tiles;
-  int32_t first_ew, num_ew;
-  int32_t stage_bytes;      // smem ring geometry of this phase (max over its GEMM jobs)
+  int32_t num_gemm, gemm_tiles;   // GEMM jobs of this phase (PhaseBlob::gj[0..num_gemm)) and their tile total
+  int32_t num_ew;                 // elementwise jobs (PhaseBlob::ej[0..num_ew)), run after the CTA's tiles
+  int32_t stage_bytes;            // smem ring geometry of this phase (max over its GEMM jobs)
   int32_t num_stages;
-  int32_t sched_off;        // < 0: tiles are strided over CTAs; else offset into MegaParams::sched of
-                            // [grid + 1 begin offsets][tile ids ...] (longest-first per CTA)
+  int32_t sched_off;              // < 0: tiles are strided over CTAs; else offset into MegaParams::sched of the
+                                  // tile-id lists (CtaTiles::begin/end index into it)
+  int32_t pad[2];
+};
+
+// Everything a CTA needs to know about one phase, contiguous in device memory.  All 256 threads copy
+// the NEXT phase's blob into shared memory while thread 0 waits in the grid barrier, so no role ever
+// chases descriptor pointers through L2 at the start of a phase.
+constexpr int kBlobGemm = 2;
+constexpr int kBlobEw = 3;
+struct alignas(16) PhaseBlob {
+  Phase ph;
+  GemmJob gj[kBlobGemm];
+  EwJob ej[kBlobEw];
+};
+
+// Tiles of one phase owned by one CTA (host-computed, longest first): ids [begin, end) of the phase's
+// list in MegaParams::sched; the first kTileSlots ids are repeated inline.
+constexpr int kTileSlots = 6;
+struct alignas(16) CtaTiles {
+  int32_t begin, end;
+  int32_t tile[kTileSlots];
 };
 
 struct MegaParams {
-  const GemmJob* gemm_jobs;
-  const EwJob* ew_jobs;
-  const Phase* phases;
+  const PhaseBlob* blobs;   // [num_phases]
+  const CtaTiles* cta_tiles;  // [num_phases][gridDim.x] (nullptr: every phase is strided)
   const void* tmaps;        // array of CUtensorMap (128 B each, 64 B aligned)
-  const int32_t* sched;     // per-phase tile schedules (see Phase::sched_off)
+  const int32_t* sched;     // per-phase tile lists (see Phase::sched_off)
   unsigned int* barrier;    // grid barrier counter (zeroed before launch)
   unsigned long long* phase_ns;  // [8 * (num_phases + 1)] globaltimer stamps written by block 0 (nullptr: off)
   int32_t num_phases;
