@@ -146,7 +146,7 @@ struct Bufs {
   void* zT[kNumHeavy]; void* dyT[kNumHeavy];
   uint32_t* keep[kNumHeavy]; uint32_t* drop;
   PlaneRef h_fm[kNumHeavy], dz_fm[kNumHeavy];
-  float* G2; float* G4;
+  void* G2; void* G4;
   PlaneRef dP_fm;
   int64_t Bs, ldw;
 };
@@ -200,12 +200,12 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
   }
   u.X_fm = take_planes(c, P, kDin, Bs);
   const int64_t zbytes = int64_t(kHidden) * Bs * (P == 1 ? 2 : 4);
-  u.drop = train ? c.take_n<uint32_t>(int64_t(kNumHeavy) * kHidden * ldw) : nullptr;
+  u.drop = nullptr;   // dropout bits are drawn where they are consumed (drop_word / drop_bits8)
   for (int l = 0; l < kNumHeavy; ++l) {
     u.h_fm[l] = take_planes(c, P, kHidden, Bs);
     if (train) {
       u.zT[l] = c.take(zbytes);
-      u.dyT[l] = large ? c.take(zbytes) : nullptr;
+      u.dyT[l] = (large && l != 4 && l != 2) ? c.take(zbytes) : nullptr;   // layers 4 / 2 keep g instead
       u.keep[l] = c.take_n<uint32_t>(int64_t(kHidden) * ldw);
       u.dz_fm[l] = take_planes(c, P, kHidden, Bs);
     } else {
@@ -214,8 +214,10 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
     }
   }
   if (train) {
-    u.G2 = c.take_n<float>(int64_t(kHidden) * Bs);
-    u.G4 = c.take_n<float>(int64_t(kHidden) * Bs);
+    // gradients kept for the residual edges: fp32 on the small path, storage type of z on the large path
+    const int64_t gbytes = int64_t(kHidden) * Bs * ((large && P == 1) ? 2 : 4);
+    u.G2 = c.take(gbytes);
+    u.G4 = c.take(gbytes);
     u.dP_fm = take_planes(c, P, kDout, Bs);
   } else {
     u.G2 = u.G4 = nullptr;
@@ -637,12 +639,7 @@ static int build_plan(b200_plan* pl) {
       for (int l = 0; l < kNumHeavy; ++l) a.nbt_w[l] = d.num_batches_tracked[l];
     }
     if (add_ew(pl, EW_PREP, a)) return 1;
-    if (pl->large) {
-      Args b = base_args(pl, 0);
-      b.keep = u.drop;
-      if (add_ew(pl, EW_DROPBITS, b)) return 1;
-      if (end_phase(pl)) return 1;
-    }
+    if (pl->large && end_phase(pl)) return 1;
     return 0;
   };
 

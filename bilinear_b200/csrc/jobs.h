@@ -42,7 +42,7 @@ enum EpiKind : int32_t {
 
 enum EwKind : int32_t {
   EW_PREP = 0,         // zero accumulators, split x into feature-major planes, bump BN counters
-  EW_DROPBITS = 1,     // pack injected uint8 masks / generate Philox bits -> [f][b/32] words
+  EW_RESERVED1 = 1,    // (dropout bits are drawn where they are consumed)
   EW_BN_FOLD = 2,      // eval: scale = g*rsqrt(rv+eps), shift = b + (bias-rm)*scale, all five layers (Args::fold)
   EW_BN_FWD_APPLY = 3, // large path: z -> h + keep bits + running stats
   EW_BN_BWD_APPLY = 4, // large path: dy,z -> dz + db
@@ -141,8 +141,9 @@ struct alignas(16) Args {
   uint32_t* keep;          // [f][ldw] bit j of word w <-> b = 32 w + j : dropout_keep & (y > 0)
   const uint32_t* drop;    // [f][ldw] dropout keep bits (nullptr => all ones)
   int64_t ldw;
-  const float* skip_in;    // dgrad: gradient arriving over the residual edge  [f][ldT] (nullptr: none)
-  float* g_out;            // dgrad: total gradient at this layer's output, kept for a later skip
+  const void* skip_in;     // backward: gradient arriving over the residual edge [f][ldT] (nullptr: none); fp32 on
+  void* g_out;             // the small path, dtype of zT on the large path.  g_out: total gradient at this
+                           // layer's output, kept for a later skip (large path: replaces dyT for that layer)
   PlaneRef skip_fm;        // fwd: residual input, feature-major planes (p == nullptr: none)
   // ---- plane output: feature-major [f][b] (every activation / gradient operand lives in this one
   // layout: K-major A operand of the wgrad GEMMs, MN-major B operand of the forward / dgrad GEMMs)

@@ -62,7 +62,8 @@ class Rounding:
     def bf16(large_batch=False):
         # large_batch (B > 256): BatchNorm needs the whole column before any element can be normalised,
         # so z (forward) and dy (backward) make one round trip through HBM between the two passes -- in
-        # bf16; the normalisation then starts from the rounded z
+        # bf16; the normalisation then starts from the rounded z.  The gradient kept for a residual edge
+        # makes the same round trip (it doubles as the stored dy of its layer)
         return Rounding(operands=True, saved_z=True, saved_dy=large_batch, fwd_z=large_batch)
 
     @staticmethod
@@ -246,7 +247,7 @@ def backward(st, cache, dP, rnd=EXACT, relu_pos=None):
         return dzr @ rnd.op(W)
 
     for blk in (1, 0):
-        skip_grad = dh                                  # out = block(h) + h
+        skip_grad = rnd.dy(dh)                          # out = block(h) + h
         dx = heavy_backward(2 + 2 * blk, dh)
         dx = heavy_backward(1 + 2 * blk, dx)
         dh = dx + skip_grad
