@@ -33,6 +33,7 @@ FLOP_PER_POSE_TRAIN = 25591808      # fwd 8 552 448 + dgrad
 FLOP_PER_POSE_FWD = 8552448
 PARAM_NUMEL = 4291632
 ADAM_BYTES_PER_STEP = 6 * 4 * PARAM_NUMEL   # p, m, v read + written (SURVEY.md section 8(d), B=64 row)
+SPACER_CYCLES = 600_000                     # ~0.3 ms at 1.9 GHz
 EVAL_BYTES_PER_POSE = 384                   # 2 x 16 x 3 x 4 read (+ 4 written when per-pose output is kept)
 
 
@@ -180,6 +181,10 @@ def timed_steps(torch, parallel, fn, steps, flusher, device):
     for a, b in evs:
         if flusher is not None:
             flusher.flush()
+        # ~0.3 ms device-side spacer: the host enqueues the start event, the step and the stop event while
+        # the GPU is still busy, so the event pair measures the step on the device and not the Python /
+        # ctypes launch path (that path is what `e2e` measures, on the wall clock)
+        torch.cuda._sleep(SPACER_CYCLES)
         a.record()
         fn()
         b.record()

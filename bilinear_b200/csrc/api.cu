@@ -27,6 +27,9 @@ struct EvalParams {
   int64_t n; int32_t n_actions;
 };
 cudaError_t launch_eval(const EvalParams& prm, int joints, bool do_m, bool do_p, cudaStream_t stream);
+cudaError_t launch_eval_tma(const EvalParams& prm, const CUtensorMap* tp, const CUtensorMap* tg, bool do_m, bool do_p,
+                            cudaStream_t stream, int* launches);
+int eval_tma_box_rows();
 }  // namespace b200
 
 using namespace b200;
@@ -898,7 +901,29 @@ static int eval_common(const float* pred, const float* gt, const float* mean, co
   prm.dist_out = dist_out; prm.pdist_out = pdist_out; prm.acc_sum = acc_sum; prm.pacc_sum = pacc_sum;
   prm.acc_cnt = reinterpret_cast<long long*>(acc_cnt);
   prm.n = n; prm.n_actions = n_actions;
-  CK(launch_eval(prm, joints, do_m, do_p, (cudaStream_t)stream));
+  // J = 16 with 16-byte aligned tensors: TMA-fed kernel ([n][48] fp32 viewed through two tensor maps
+  // that travel in the kernel parameters); otherwise (J = 17: 204-byte rows) the register-staged one
+  EncodeTiledFn enc = get_encode();
+  if (joints == 16 && enc && n < (int64_t(1) << 31) && reinterpret_cast<uintptr_t>(pred) % 16 == 0 &&
+      reinterpret_cast<uintptr_t>(gt) % 16 == 0) {
+    CUtensorMap tm[2];
+    const void* bases[2] = {pred, gt};
+    for (int i = 0; i < 2; ++i) {
+      cuuint64_t dims[2] = {48, cuuint64_t(n)};
+      cuuint64_t strides[1] = {192};
+      cuuint32_t box[2] = {16, cuuint32_t(eval_tma_box_rows())};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(bases[i]), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (eval) -> %d", int(r));
+    }
+    int launches = 1;
+    CK(launch_eval_tma(prm, &tm[0], &tm[1], do_m, do_p, (cudaStream_t)stream, &launches));
+    g_launches.fetch_add(launches - 1);
+  } else {
+    CK(launch_eval(prm, joints, do_m, do_p, (cudaStream_t)stream));
+  }
   g_launches.fetch_add(1);
   return 0;
 }

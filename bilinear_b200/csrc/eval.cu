@@ -14,6 +14,7 @@
 //     distances.  Degenerate poses (repeated top eigenvalue, zero extent) fall back to a cyclic
 //     Jacobi eigen-solver / the unaligned distance, so the result is always finite.
 //   - per-action sums are accumulated in fp64 in shared memory and flushed once per CTA.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -153,6 +154,111 @@ __device__ __forceinline__ void horn_top(const float S[3][3], float& lam, float 
   }
 }
 
+// Per-pose metrics from un-normalised coordinates (mm).  P and G are modified (centred) when DO_P.
+template <int J, bool DO_M, bool DO_P>
+__device__ __forceinline__ void pose_metrics(float* P, float* G, float& dist, float& pdist) {
+  constexpr int W = 3 * J;
+  dist = 0.f;
+  pdist = 0.f;
+  if (DO_M) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const float dx = P[3 * j] - G[3 * j], dy = P[3 * j + 1] - G[3 * j + 1], dz = P[3 * j + 2] - G[3 * j + 2];
+      dist += sqrtf(dx * dx + dy * dy + dz * dz);        // valid_bilinear.py:60
+    }
+  }
+  if (DO_P) {
+    float mp[3] = {0.f, 0.f, 0.f}, mg[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { mp[a] += P[3 * j + a]; mg[a] += G[3 * j + a]; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { mp[a] *= (1.f / J); mg[a] *= (1.f / J); }
+    float rawP2 = 0.f, rawG2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < W; ++w) { rawP2 += P[w] * P[w]; rawG2 += G[w] * G[w]; }
+    float nP2 = 0.f, nG2 = 0.f;
+    float S[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      float pc[3], gc[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        pc[a] = P[3 * j + a] - mp[a];
+        gc[a] = G[3 * j + a] - mg[a];
+        P[3 * j + a] = pc[a];
+        G[3 * j + a] = gc[a];
+        nP2 += pc[a] * pc[a];
+        nG2 += gc[a] * gc[a];
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) S[a][b] += pc[a] * gc[b];
+    }
+    // zero-extent convention shared with oracle/pose_metrics.py (DEGENERATE_REL)
+    if (nP2 > 1e-10f * rawP2 && nG2 > 1e-10f * rawG2) {
+      const float inv = rsqrtf(nP2) * rsqrtf(nG2);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) S[a][b] *= inv;
+      float lam, q[4];
+      horn_top(S, lam, q);
+      const float scale = lam * sqrtf(nG2) * rsqrtf(nP2);   // tr * nG / nP (Appendix B)
+      const float q0 = q[0], qx = q[1], qy = q[2], qz = q[3];
+      const float R00 = q0 * q0 + qx * qx - qy * qy - qz * qz, R01 = 2.f * (qx * qy - q0 * qz),
+                  R02 = 2.f * (qx * qz + q0 * qy);
+      const float R10 = 2.f * (qy * qx + q0 * qz), R11 = q0 * q0 - qx * qx + qy * qy - qz * qz,
+                  R12 = 2.f * (qy * qz - q0 * qx);
+      const float R20 = 2.f * (qz * qx - q0 * qy), R21 = 2.f * (qz * qy + q0 * qx),
+                  R22 = q0 * q0 - qx * qx - qy * qy + qz * qz;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const float px = P[3 * j], py = P[3 * j + 1], pz = P[3 * j + 2];
+        const float ax = scale * (R00 * px + R01 * py + R02 * pz) - G[3 * j];
+        const float ay = scale * (R10 * px + R11 * py + R12 * pz) - G[3 * j + 1];
+        const float az = scale * (R20 * px + R21 * py + R22 * pz) - G[3 * j + 2];
+        pdist += sqrtf(ax * ax + ay * ay + az * az);
+      }
+    } else {
+      // zero-extent pose: alignment undefined -> unaligned distance of the (uncentred) poses
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const float dx = (P[3 * j] + mp[0]) - (G[3 * j] + mg[0]);
+        const float dy = (P[3 * j + 1] + mp[1]) - (G[3 * j + 1] + mg[1]);
+        const float dz = (P[3 * j + 2] + mp[2]) - (G[3 * j + 2] + mg[2]);
+        pdist += sqrtf(dx * dx + dy * dy + dz * dz);
+      }
+    }
+  }
+}
+
+// Per-action accumulation (valid_bilinear.py:61-70) without contended atomics: the warp walks over the
+// distinct action ids it holds; for each, the lanes of that action are summed with shuffles (fp64, like
+// the reference's np.double accumulation) and ONE lane adds the result to the warp's private buckets.
+template <bool DO_M, bool DO_P>
+__device__ __forceinline__ void warp_accumulate(bool valid, int act, float dist, float pdist, double* wS, double* wPS,
+                                                unsigned long long* wC, int lane) {
+  uint32_t todo = __ballot_sync(0xffffffffu, valid);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int a = __shfl_sync(0xffffffffu, act, leader);
+    const bool mine = valid && act == a;
+    const uint32_t m = __ballot_sync(0xffffffffu, mine);
+    double s = (DO_M && mine) ? double(dist) : 0.0, ps = (DO_P && mine) ? double(pdist) : 0.0;
+    if (DO_M) s = warp_sum(s);
+    if (DO_P) ps = warp_sum(ps);
+    if (lane == leader) {
+      if (DO_M) wS[a] += s;
+      if (DO_P) wPS[a] += ps;
+      wC[a] += (unsigned long long)__popc(m);
+    }
+    todo &= ~m;
+  }
+}
+
 template <int J, bool DO_M, bool DO_P>
 __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams prm) {
   constexpr int W = 3 * J;          // floats per pose
@@ -163,10 +269,10 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams prm
   float* sG = sm + CH * PITCH;
   float* sMean = sG + CH * PITCH;
   float* sStd = sMean + W;
-  __shared__ double accS[kMaxActions], accPS[kMaxActions];
-  __shared__ unsigned long long accC[kMaxActions];
+  __shared__ double accS[kEvalThreads / 32][kMaxActions], accPS[kEvalThreads / 32][kMaxActions];
+  __shared__ unsigned long long accC[kEvalThreads / 32][kMaxActions];
   const int tid = threadIdx.x;
-  for (int i = tid; i < kMaxActions; i += CH) { accS[i] = 0.0; accPS[i] = 0.0; accC[i] = 0ull; }
+  for (int i = tid; i < (kEvalThreads / 32) * kMaxActions; i += CH) { (&accS[0][0])[i] = 0.0; (&accPS[0][0])[i] = 0.0; (&accC[0][0])[i] = 0ull; }
   const bool unnorm = prm.mean != nullptr;
   for (int i = tid; i < W; i += CH) {
     sMean[i] = unnorm ? prm.mean[i] : 0.f;
@@ -220,106 +326,252 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams prm
     }
     __syncthreads();
 
-    if (tid < np) {
-      float P[W], G[W];
-#pragma unroll
-      for (int w = 0; w < W; ++w) {
-        P[w] = sStd[w] * sP[tid * PITCH + w] + sMean[w];   // valid_bilinear.py:53
-        G[w] = sStd[w] * sG[tid * PITCH + w] + sMean[w];   // valid_bilinear.py:54
-      }
+    {
+      const bool valid = tid < np;
       float dist = 0.f, pdist = 0.f;
-      if (DO_M) {
+      int act = 0;
+      if (valid) {
+        float P[W], G[W];
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const float dx = P[3 * j] - G[3 * j], dy = P[3 * j + 1] - G[3 * j + 1], dz = P[3 * j + 2] - G[3 * j + 2];
-          dist += sqrtf(dx * dx + dy * dy + dz * dz);        // valid_bilinear.py:60
+        for (int w = 0; w < W; ++w) {
+          P[w] = sStd[w] * sP[tid * PITCH + w] + sMean[w];   // valid_bilinear.py:53
+          G[w] = sStd[w] * sG[tid * PITCH + w] + sMean[w];   // valid_bilinear.py:54
         }
+        pose_metrics<J, DO_M, DO_P>(P, G, dist, pdist);
+        const int64_t gi = p0 + tid;
+        if (DO_M && prm.dist_out) prm.dist_out[gi] = dist;
+        if (DO_P && prm.pdist_out) prm.pdist_out[gi] = pdist;
+        act = prm.action ? prm.action[gi] : 0;
+        act = min(max(act, 0), prm.n_actions - 1);
       }
-      if (DO_P) {
-        float mp[3] = {0.f, 0.f, 0.f}, mg[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < J; ++j)
-#pragma unroll
-          for (int a = 0; a < 3; ++a) { mp[a] += P[3 * j + a]; mg[a] += G[3 * j + a]; }
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { mp[a] *= (1.f / J); mg[a] *= (1.f / J); }
-        float rawP2 = 0.f, rawG2 = 0.f;
-#pragma unroll
-        for (int w = 0; w < W; ++w) { rawP2 += P[w] * P[w]; rawG2 += G[w] * G[w]; }
-        float nP2 = 0.f, nG2 = 0.f;
-        float S[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          float pc[3], gc[3];
-#pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            pc[a] = P[3 * j + a] - mp[a];
-            gc[a] = G[3 * j + a] - mg[a];
-            P[3 * j + a] = pc[a];
-            G[3 * j + a] = gc[a];
-            nP2 += pc[a] * pc[a];
-            nG2 += gc[a] * gc[a];
-          }
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int b = 0; b < 3; ++b) S[a][b] += pc[a] * gc[b];
-        }
-        // zero-extent convention shared with oracle/pose_metrics.py (DEGENERATE_REL)
-        if (nP2 > 1e-10f * rawP2 && nG2 > 1e-10f * rawG2) {
-          const float inv = rsqrtf(nP2) * rsqrtf(nG2);
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int b = 0; b < 3; ++b) S[a][b] *= inv;
-          float lam, q[4];
-          horn_top(S, lam, q);
-          const float scale = lam * sqrtf(nG2) * rsqrtf(nP2);   // tr * nG / nP (Appendix B)
-          const float q0 = q[0], qx = q[1], qy = q[2], qz = q[3];
-          const float R00 = q0 * q0 + qx * qx - qy * qy - qz * qz, R01 = 2.f * (qx * qy - q0 * qz),
-                      R02 = 2.f * (qx * qz + q0 * qy);
-          const float R10 = 2.f * (qy * qx + q0 * qz), R11 = q0 * q0 - qx * qx + qy * qy - qz * qz,
-                      R12 = 2.f * (qy * qz - q0 * qx);
-          const float R20 = 2.f * (qz * qx - q0 * qy), R21 = 2.f * (qz * qy + q0 * qx),
-                      R22 = q0 * q0 - qx * qx - qy * qy + qz * qz;
-#pragma unroll
-          for (int j = 0; j < J; ++j) {
-            const float px = P[3 * j], py = P[3 * j + 1], pz = P[3 * j + 2];
-            const float ax = scale * (R00 * px + R01 * py + R02 * pz) - G[3 * j];
-            const float ay = scale * (R10 * px + R11 * py + R12 * pz) - G[3 * j + 1];
-            const float az = scale * (R20 * px + R21 * py + R22 * pz) - G[3 * j + 2];
-            pdist += sqrtf(ax * ax + ay * ay + az * az);
-          }
-        } else {
-          // zero-extent pose: alignment undefined -> unaligned distance of the (uncentred) poses
-#pragma unroll
-          for (int j = 0; j < J; ++j) {
-            const float dx = (P[3 * j] + mp[0]) - (G[3 * j] + mg[0]);
-            const float dy = (P[3 * j + 1] + mp[1]) - (G[3 * j + 1] + mg[1]);
-            const float dz = (P[3 * j + 2] + mp[2]) - (G[3 * j + 2] + mg[2]);
-            pdist += sqrtf(dx * dx + dy * dy + dz * dz);
-          }
-        }
-      }
-      const int64_t gi = p0 + tid;
-      if (DO_M && prm.dist_out) prm.dist_out[gi] = dist;
-      if (DO_P && prm.pdist_out) prm.pdist_out[gi] = pdist;
-      int act = prm.action ? prm.action[gi] : 0;
-      act = min(max(act, 0), prm.n_actions - 1);
-      if (DO_M) atomicAdd(&accS[act], double(dist));      // valid_bilinear.py:68 (np.double accumulation)
-      if (DO_P) atomicAdd(&accPS[act], double(pdist));
-      atomicAdd(&accC[act], 1ull);
+      const int wi = tid >> 5;
+      warp_accumulate<DO_M, DO_P>(valid, act, dist, pdist, accS[wi], accPS[wi], accC[wi], tid & 31);
     }
     __syncthreads();
   }
   for (int i = tid; i < prm.n_actions; i += CH) {
-    if (accC[i] != 0ull) {
-      if (DO_M && prm.acc_sum) atomicAdd(prm.acc_sum + i, accS[i]);
-      if (DO_P && prm.pacc_sum) atomicAdd(prm.pacc_sum + i, accPS[i]);
-      if (prm.acc_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(prm.acc_cnt) + i, accC[i]);
+    double sm = 0.0, ps = 0.0;
+    unsigned long long c = 0ull;
+    for (int w = 0; w < kEvalThreads / 32; ++w) { sm += accS[w][i]; ps += accPS[w][i]; c += accC[w][i]; }
+    if (c != 0ull) {
+      if (DO_M && prm.acc_sum) atomicAdd(prm.acc_sum + i, sm);
+      if (DO_P && prm.pacc_sum) atomicAdd(prm.pacc_sum + i, ps);
+      if (prm.acc_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(prm.acc_cnt) + i, c);
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// J = 16 fast path: TMA-fed.  128 poses of both tensors arrive as six 2-D boxes of {16 floats, 128
+// poses} (64-byte rows, SWIZZLE_64B), so that thread r can pull ITS pose out of shared memory with
+// conflict-free 128-bit loads (unit u of row r sits at u ^ ((r >> 1) & 3)).  A CTA owns ONE 48 KB
+// buffer: as soon as every thread holds its pose in registers the buffer is handed back to the TMA
+// unit for the next chunk, which lands while the per-pose math runs -- 4 CTAs (16 warps) per SM hide
+// the serial parts of the Procrustes solve, and no data passes through registers on its way into
+// shared memory.  Per-action sums: see action_reduce_kernel (two-kernel scheme) or, when the caller
+// keeps no per-pose output, the in-kernel warp walk.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTmaPoses = kEvalThreads;             // poses per chunk
+constexpr int kSubBytes = kTmaPoses * 64;           // one 16-float column group of one tensor
+constexpr int kStageBytes = 6 * kSubBytes;          // 3 groups x {pred, gt} = 48 KB
+
+template <bool DO_M, bool DO_P, bool ACC>
+__global__ void __launch_bounds__(kEvalThreads, 4)
+eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_constant__ CUtensorMap tm_gt, const EvalParams prm) {
+  constexpr int J = 16, W = 48;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  __shared__ uint64_t full;
+  __shared__ float sMean[W], sStd[W];
+  __shared__ double accS[ACC ? kEvalThreads / 32 : 1][ACC ? kMaxActions : 1], accPS[ACC ? kEvalThreads / 32 : 1][ACC ? kMaxActions : 1];
+  __shared__ unsigned long long accC[ACC ? kEvalThreads / 32 : 1][ACC ? kMaxActions : 1];
+  const int tid = threadIdx.x;
+  if (ACC) {
+    for (int i = tid; i < (kEvalThreads / 32) * kMaxActions; i += kEvalThreads) {
+      (&accS[0][0])[i] = 0.0; (&accPS[0][0])[i] = 0.0; (&accC[0][0])[i] = 0ull;
+    }
+  }
+  const bool unnorm = prm.mean != nullptr;
+  for (int i = tid; i < W; i += kEvalThreads) {
+    sMean[i] = unnorm ? prm.mean[i] : 0.f;
+    sStd[i] = unnorm ? prm.stddev[i] : 1.f;
+  }
+  if (tid == 0) {
+    mbar_init(&full, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int64_t nchunks = (prm.n + kTmaPoses - 1) / kTmaPoses;
+  auto issue = [&](int64_t ch) {
+    mbar_expect_tx(&full, kStageBytes);
+    const int row = int(ch * kTmaPoses);
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      tma_load_2d(smem + g * kSubBytes, &tm_pred, &full, 16 * g, row);
+      tma_load_2d(smem + (3 + g) * kSubBytes, &tm_gt, &full, 16 * g, row);
+    }
+  };
+  if (tid == 0 && int64_t(blockIdx.x) < nchunks) issue(blockIdx.x);
+  uint32_t parity = 0;
+  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, parity ^= 1u) {
+    mbar_wait(&full, parity, 900);
+    float4 pr[12], gr[12];
+    {
+      const uint8_t* st = smem + tid * 64;
+      const int sw = (tid >> 1) & 3;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          pr[4 * g + u] = *reinterpret_cast<const float4*>(st + g * kSubBytes + ((u ^ sw) << 4));
+          gr[4 * g + u] = *reinterpret_cast<const float4*>(st + (3 + g) * kSubBytes + ((u ^ sw) << 4));
+        }
+      }
+    }
+    __syncthreads();   // every thread holds its pose: the buffer goes back to the TMA unit
+    if (tid == 0 && ch + gridDim.x < nchunks) {
+      fence_proxy_async_all();
+      issue(ch + gridDim.x);
+    }
+    const int64_t p0 = ch * kTmaPoses;
+    const int np = int(min(int64_t(kTmaPoses), prm.n - p0));
+    const bool valid = tid < np;
+    float dist = 0.f, pdist = 0.f;
+    int act = 0;
+    if (valid) {
+      float P[W], G[W];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int w = 4 * k;
+        P[w] = sStd[w] * pr[k].x + sMean[w];             // valid_bilinear.py:53
+        P[w + 1] = sStd[w + 1] * pr[k].y + sMean[w + 1];
+        P[w + 2] = sStd[w + 2] * pr[k].z + sMean[w + 2];
+        P[w + 3] = sStd[w + 3] * pr[k].w + sMean[w + 3];
+        G[w] = sStd[w] * gr[k].x + sMean[w];             // valid_bilinear.py:54
+        G[w + 1] = sStd[w + 1] * gr[k].y + sMean[w + 1];
+        G[w + 2] = sStd[w + 2] * gr[k].z + sMean[w + 2];
+        G[w + 3] = sStd[w + 3] * gr[k].w + sMean[w + 3];
+      }
+      pose_metrics<J, DO_M, DO_P>(P, G, dist, pdist);
+      const int64_t gi = p0 + tid;
+      if (DO_M && prm.dist_out) prm.dist_out[gi] = dist;
+      if (DO_P && prm.pdist_out) prm.pdist_out[gi] = pdist;
+      if (ACC) {
+        act = prm.action ? prm.action[gi] : 0;
+        act = min(max(act, 0), prm.n_actions - 1);
+      }
+    }
+    if (ACC) {
+      const int wi = tid >> 5;
+      warp_accumulate<DO_M, DO_P>(valid, act, dist, pdist, accS[wi], accPS[wi], accC[wi], tid & 31);
+    }
+  }
+  if (ACC) {
+    __syncthreads();
+    for (int i = tid; i < prm.n_actions; i += kEvalThreads) {
+      double sm = 0.0, ps = 0.0;
+      unsigned long long c = 0ull;
+      for (int w = 0; w < kEvalThreads / 32; ++w) { sm += accS[w][i]; ps += accPS[w][i]; c += accC[w][i]; }
+      if (c != 0ull) {
+        if (DO_M && prm.acc_sum) atomicAdd(prm.acc_sum + i, sm);
+        if (DO_P && prm.pacc_sum) atomicAdd(prm.pacc_sum + i, ps);
+        if (prm.acc_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(prm.acc_cnt) + i, c);
+      }
+    }
+  }
+}
+
+// Second kernel of the two-kernel scheme (valid_bilinear.py:61-70): per-action fp64 sums of the per-pose
+// results.  Reads 4 B (action) + 4 / 8 B (per-pose sums) per pose; every thread keeps private fp64
+// buckets in registers (NA <= 16: predicated adds, no atomics, no shuffles in the loop).
+constexpr int kRedThreads = 256;
+constexpr int kRedNA = 16;
+template <bool DO_M, bool DO_P>
+__global__ void __launch_bounds__(kRedThreads) action_reduce_kernel(const EvalParams prm) {
+  double s[kRedNA], ps[kRedNA];
+  unsigned int c[kRedNA];
+#pragma unroll
+  for (int a = 0; a < kRedNA; ++a) { s[a] = 0.0; ps[a] = 0.0; c[a] = 0u; }
+  const int64_t stride = int64_t(gridDim.x) * kRedThreads;
+  for (int64_t i = int64_t(blockIdx.x) * kRedThreads + threadIdx.x; i < prm.n; i += stride) {
+    int act = prm.action ? __ldcs(prm.action + i) : 0;
+    act = min(max(act, 0), prm.n_actions - 1);
+    const double d = DO_M ? double(__ldcs(prm.dist_out + i)) : 0.0;
+    const double pd = DO_P ? double(__ldcs(prm.pdist_out + i)) : 0.0;
+#pragma unroll
+    for (int a = 0; a < kRedNA; ++a) {
+      const bool m = act == a;
+      if (DO_M) s[a] += m ? d : 0.0;
+      if (DO_P) ps[a] += m ? pd : 0.0;
+      c[a] += m ? 1u : 0u;
+    }
+  }
+  __shared__ double bs[kRedThreads / 32][kRedNA], bps[kRedThreads / 32][kRedNA];
+  __shared__ unsigned long long bc[kRedThreads / 32][kRedNA];
+  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int a = 0; a < kRedNA; ++a) {
+    const double ws = DO_M ? warp_sum(s[a]) : 0.0, wps = DO_P ? warp_sum(ps[a]) : 0.0;
+    unsigned int wc = c[a];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wc += __shfl_xor_sync(0xffffffffu, wc, o);
+    if (lane == 0) { bs[wi][a] = ws; bps[wi][a] = wps; bc[wi][a] = wc; }
+  }
+  __syncthreads();
+  if (threadIdx.x < prm.n_actions && threadIdx.x < kRedNA) {
+    double sm = 0.0, psm = 0.0;
+    unsigned long long cc = 0ull;
+    for (int w = 0; w < kRedThreads / 32; ++w) { sm += bs[w][threadIdx.x]; psm += bps[w][threadIdx.x]; cc += bc[w][threadIdx.x]; }
+    if (cc != 0ull) {
+      if (DO_M && prm.acc_sum) atomicAdd(prm.acc_sum + threadIdx.x, sm);
+      if (DO_P && prm.pacc_sum) atomicAdd(prm.pacc_sum + threadIdx.x, psm);
+      if (prm.acc_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(prm.acc_cnt) + threadIdx.x, cc);
+    }
+  }
+}
+
+template <bool DO_M, bool DO_P, bool ACC>
+static cudaError_t launch_eval_tma_t(const EvalParams& prm, const CUtensorMap& tp, const CUtensorMap& tg, cudaStream_t stream) {
+  const size_t smem = size_t(kStageBytes) + 1024;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(eval_kernel_tma<DO_M, DO_P, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t nchunks = (prm.n + kTmaPoses - 1) / kTmaPoses;
+  const int grid = int(std::max<int64_t>(1, std::min<int64_t>(nchunks, int64_t(sms) * 4)));
+  eval_kernel_tma<DO_M, DO_P, ACC><<<grid, kEvalThreads, smem, stream>>>(tp, tg, prm);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || ACC) return e;
+  const int rgrid = int(std::max<int64_t>(1, std::min<int64_t>((prm.n + kRedThreads - 1) / kRedThreads, int64_t(sms) * 2)));
+  action_reduce_kernel<DO_M, DO_P><<<rgrid, kRedThreads, 0, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+// tp / tg: tensor maps of pred / gt viewed as [n][48] fp32 with box {16, 128} and SWIZZLE_64B (encoded by
+// the caller, api.cu); J = 16 only.
+cudaError_t launch_eval_tma(const EvalParams& prm, const CUtensorMap* tp, const CUtensorMap* tg, bool do_m, bool do_p,
+                            cudaStream_t stream, int* launches) {
+  // two-kernel scheme when the per-pose results the caller keeps are enough to rebuild the per-action
+  // sums (and there are at most 16 buckets); otherwise the sums are taken inside the kernel
+  const bool two = prm.n_actions <= kRedNA && (!do_m || prm.dist_out) && (!do_p || prm.pdist_out);
+  *launches = two ? 2 : 1;
+  if (two) {
+    if (do_m && do_p) return launch_eval_tma_t<true, true, false>(prm, *tp, *tg, stream);
+    if (do_m) return launch_eval_tma_t<true, false, false>(prm, *tp, *tg, stream);
+    return launch_eval_tma_t<false, true, false>(prm, *tp, *tg, stream);
+  }
+  if (do_m && do_p) return launch_eval_tma_t<true, true, true>(prm, *tp, *tg, stream);
+  if (do_m) return launch_eval_tma_t<true, false, true>(prm, *tp, *tg, stream);
+  return launch_eval_tma_t<false, true, true>(prm, *tp, *tg, stream);
+}
+int eval_tma_box_rows() { return kTmaPoses; }
 
 template <int J, bool DO_M, bool DO_P>
 static cudaError_t launch_eval_t(const EvalParams& prm, cudaStream_t stream) {
