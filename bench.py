@@ -154,11 +154,19 @@ class TrainLoop:
         return out
 
     def one_e2e(self):
+        """train_bilinear.py:62-88 through the public API with pinned HOST batches: H2D of x and y, the step,
+        and the loss read back (train_bilinear.py:88) every iteration."""
         k = self.i % len(self.hx)
+        if self.world == 1:
+            self._lr()
+            self.i += 1
+            loss, _ = self.net.train_step_host(self.opt, self.hx[k], self.hy[k], max_norm=1.0)
+            self.step += 1
+            return loss
         x = self.hx[k].to(self.device, non_blocking=True)
         y = self.hy[k].to(self.device, non_blocking=True)
         loss, _ = self.one(x, y)
-        return float(loss.item())                       # train_bilinear.py:88: loss read back every step
+        return float(loss.item())
 
 
 class L2Flusher:

@@ -59,6 +59,9 @@ _SIGS = {
     "b200_forward_train": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
     "b200_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200_train_step": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.POINTER(AdamArgs), C.c_int32, C.c_void_p]),
+    "b200_train_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TrainArgs), C.POINTER(AdamArgs),
+                                       C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200_forward_eval_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200_adam_step": (C.c_int, [C.c_void_p, C.POINTER(AdamArgs), C.c_void_p, C.c_void_p]),
     "b200_mpjpe": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 4),
     "b200_pmpjpe": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 4),

@@ -141,6 +141,7 @@ struct Bufs {
   uint16_t* wplanes; int64_t wplane_stride;   // bf16 planes of the whole flat parameter buffer
   float* part;                       // small path: [kSmallSplit][1024][Bs] fp32 partial sums
   float* x_save;                     // small path: copy of the input batch [Bs][32] fp32
+  float* x_stage; float* y_stage; float* p_stage; float* scalars;   // device ends of the *_host entry points
   uint8_t* acc_base; int64_t acc_bytes;
   double* loss_acc; double* gnorm2; double* stats_f[kNumHeavy]; double* stats_b[kNumHeavy];
   float* save_mean[kNumHeavy]; float* save_rstd[kNumHeavy]; float* scale[kNumHeavy]; float* shift[kNumHeavy];
@@ -179,6 +180,10 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
   u.fold_tab = c.take_n<FoldTab>(1);
   u.part = large ? nullptr : c.take_n<float>(int64_t(kSmallSplit) * kHidden * Bs);
   u.x_save = large ? nullptr : c.take_n<float>(Bs * kDin);
+  u.x_stage = c.take_n<float>(Bs * kDin);
+  u.y_stage = c.take_n<float>(Bs * kDout);
+  u.p_stage = c.take_n<float>(Bs * kDout);
+  u.scalars = c.take_n<float>(16);
   // accumulators cleared at the start of every step (one contiguous region)
   const int64_t acc0 = (c.off + 1023) & ~int64_t(1023);
   u.loss_acc = c.take_n<double>(16);
@@ -247,6 +252,7 @@ struct b200_plan {
   std::vector<int32_t> sched;
   Sched s_refresh, s_eval, s_fwd, s_bwd, s_step, s_update;
   PhaseBlob cur;
+  uint32_t bar_count = 0;   // grid-barrier arrivals so far (device counter is monotonic)
   int last_first = 0, last_count = 0;
 };
 
@@ -745,7 +751,8 @@ static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, c
   p.num_phases = count;
   p.dyn = dyn;
   const bool coop = count > 1;
-  if (coop) CK(cudaMemsetAsync(pl->u.barrier, 0, 4, stream));
+  p.bar_base = pl->bar_count;
+  pl->bar_count += uint32_t(pl->sms) * uint32_t(count - 1);
   CK(launch_mega(p, pl->sms, coop, stream));
   g_launches.fetch_add(1);
   return 0;
@@ -831,6 +838,7 @@ int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
     const FoldTab tab = make_fold_tab(pl);
     e = cudaMemcpy(pl->u.fold_tab, &tab, sizeof tab, cudaMemcpyHostToDevice);
   }
+  if (e == cudaSuccess) e = cudaMemset(pl->u.barrier, 0, 256);
   if (e != cudaSuccess) { delete pl; return fail("plan upload failed: %s", cudaGetErrorString(e)); }
   *out = pl;
   return 0;
@@ -876,6 +884,33 @@ int b200_train_step(b200_plan* plan, const b200_train_args* targs, const b200_ad
   int count = plan->s_step.count - (update ? 0 : 1);
   int rc = run_sched(plan, plan->s_step, count, d, (cudaStream_t)stream);
   if (rc) return rc;
+  return 0;
+}
+
+int b200_train_step_host(b200_plan* plan, const float* x_host, const float* y_host, const b200_train_args* targs,
+                         const b200_adam_args* aargs, int32_t update, float* out_host, void* stream) {
+  if (!plan || !x_host || !y_host || !targs || !out_host) return fail("null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t B = size_t(plan->B);
+  CK(cudaMemcpyAsync(plan->u.x_stage, x_host, B * kDin * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(plan->u.y_stage, y_host, B * kDout * sizeof(float), cudaMemcpyHostToDevice, st));
+  b200_train_args t = *targs;
+  t.x = plan->u.x_stage; t.y = plan->u.y_stage;
+  t.loss_out = plan->u.scalars; t.gnorm_out = plan->u.scalars + 1;
+  int rc = b200_train_step(plan, &t, aargs, update, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out_host, plan->u.scalars, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+int b200_forward_eval_host(b200_plan* plan, const float* x_host, float* p_host, void* stream) {
+  if (!plan || !x_host || !p_host) return fail("null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t B = size_t(plan->B);
+  CK(cudaMemcpyAsync(plan->u.x_stage, x_host, B * kDin * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = b200_forward_eval(plan, plan->u.x_stage, plan->u.p_stage, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(p_host, plan->u.p_stage, B * kDout * sizeof(float), cudaMemcpyDeviceToHost, st));
   return 0;
 }
 

@@ -79,6 +79,9 @@ __device__ __noinline__ void jacobi4_top(const float* Nm, float& lam, float* q) 
   for (int k = 0; k < 4; ++k) q[k] = V[k][best];
 }
 
+// sqrt(x) for x >= 0 as x * rsqrt(x) (2 ulp; distances are ~1e1..1e3 mm and the tolerance is 0.05 mm)
+__device__ __forceinline__ float fast_sqrt(float x) { return x > 0.f ? x * rsqrtf(x) : 0.f; }
+
 __device__ __forceinline__ float det3(float a, float b, float c, float d, float e, float f, float g, float h, float i) {
   return a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
 }
@@ -116,7 +119,7 @@ __device__ __forceinline__ void horn_top(const float S[3][3], float& lam, float 
     const float pv = (l2 + c2) * l2 + c1 * l + c0;
     const float dv = (4.f * l2 + 2.f * c2) * l + c1;
     if (!(fabsf(dv) > 1e-30f)) break;
-    const float step = pv / dv;
+    const float step = __fdividef(pv, dv);   // Newton corrects its own rounding: an approximate quotient is enough
     l -= step;
     if (fabsf(step) < 1e-7f * fabsf(l)) break;
   }
@@ -164,7 +167,7 @@ __device__ __forceinline__ void pose_metrics(float* P, float* G, float& dist, fl
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       const float dx = P[3 * j] - G[3 * j], dy = P[3 * j + 1] - G[3 * j + 1], dz = P[3 * j + 2] - G[3 * j + 2];
-      dist += sqrtf(dx * dx + dy * dy + dz * dz);        // valid_bilinear.py:60
+      dist += fast_sqrt(dx * dx + dy * dy + dz * dz);    // valid_bilinear.py:60
     }
   }
   if (DO_P) {
@@ -175,9 +178,6 @@ __device__ __forceinline__ void pose_metrics(float* P, float* G, float& dist, fl
       for (int a = 0; a < 3; ++a) { mp[a] += P[3 * j + a]; mg[a] += G[3 * j + a]; }
 #pragma unroll
     for (int a = 0; a < 3; ++a) { mp[a] *= (1.f / J); mg[a] *= (1.f / J); }
-    float rawP2 = 0.f, rawG2 = 0.f;
-#pragma unroll
-    for (int w = 0; w < W; ++w) { rawP2 += P[w] * P[w]; rawG2 += G[w] * G[w]; }
     float nP2 = 0.f, nG2 = 0.f;
     float S[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
 #pragma unroll
@@ -197,7 +197,10 @@ __device__ __forceinline__ void pose_metrics(float* P, float* G, float& dist, fl
 #pragma unroll
         for (int b = 0; b < 3; ++b) S[a][b] += pc[a] * gc[b];
     }
-    // zero-extent convention shared with oracle/pose_metrics.py (DEGENERATE_REL)
+    // zero-extent convention shared with oracle/pose_metrics.py (DEGENERATE_REL); the raw second moment
+    // is sum p^2 = sum (p - m)^2 + J |m|^2
+    const float rawP2 = nP2 + float(J) * (mp[0] * mp[0] + mp[1] * mp[1] + mp[2] * mp[2]);
+    const float rawG2 = nG2 + float(J) * (mg[0] * mg[0] + mg[1] * mg[1] + mg[2] * mg[2]);
     if (nP2 > 1e-10f * rawP2 && nG2 > 1e-10f * rawG2) {
       const float inv = rsqrtf(nP2) * rsqrtf(nG2);
 #pragma unroll
@@ -208,19 +211,21 @@ __device__ __forceinline__ void pose_metrics(float* P, float* G, float& dist, fl
       horn_top(S, lam, q);
       const float scale = lam * sqrtf(nG2) * rsqrtf(nP2);   // tr * nG / nP (Appendix B)
       const float q0 = q[0], qx = q[1], qy = q[2], qz = q[3];
-      const float R00 = q0 * q0 + qx * qx - qy * qy - qz * qz, R01 = 2.f * (qx * qy - q0 * qz),
-                  R02 = 2.f * (qx * qz + q0 * qy);
-      const float R10 = 2.f * (qy * qx + q0 * qz), R11 = q0 * q0 - qx * qx + qy * qy - qz * qz,
-                  R12 = 2.f * (qy * qz - q0 * qx);
-      const float R20 = 2.f * (qz * qx - q0 * qy), R21 = 2.f * (qz * qy + q0 * qx),
-                  R22 = q0 * q0 - qx * qx - qy * qy + qz * qz;
+      // scale * R (the similarity transform applied to the centred prediction)
+      const float s2 = 2.f * scale;
+      const float R00 = scale * (q0 * q0 + qx * qx - qy * qy - qz * qz), R01 = s2 * (qx * qy - q0 * qz),
+                  R02 = s2 * (qx * qz + q0 * qy);
+      const float R10 = s2 * (qy * qx + q0 * qz), R11 = scale * (q0 * q0 - qx * qx + qy * qy - qz * qz),
+                  R12 = s2 * (qy * qz - q0 * qx);
+      const float R20 = s2 * (qz * qx - q0 * qy), R21 = s2 * (qz * qy + q0 * qx),
+                  R22 = scale * (q0 * q0 - qx * qx - qy * qy + qz * qz);
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const float px = P[3 * j], py = P[3 * j + 1], pz = P[3 * j + 2];
-        const float ax = scale * (R00 * px + R01 * py + R02 * pz) - G[3 * j];
-        const float ay = scale * (R10 * px + R11 * py + R12 * pz) - G[3 * j + 1];
-        const float az = scale * (R20 * px + R21 * py + R22 * pz) - G[3 * j + 2];
-        pdist += sqrtf(ax * ax + ay * ay + az * az);
+        const float ax = (R00 * px + R01 * py + R02 * pz) - G[3 * j];
+        const float ay = (R10 * px + R11 * py + R12 * pz) - G[3 * j + 1];
+        const float az = (R20 * px + R21 * py + R22 * pz) - G[3 * j + 2];
+        pdist += fast_sqrt(ax * ax + ay * ay + az * az);
       }
     } else {
       // zero-extent pose: alignment undefined -> unaligned distance of the (uncentred) poses
@@ -229,7 +234,7 @@ __device__ __forceinline__ void pose_metrics(float* P, float* G, float& dist, fl
         const float dx = (P[3 * j] + mp[0]) - (G[3 * j] + mg[0]);
         const float dy = (P[3 * j + 1] + mp[1]) - (G[3 * j + 1] + mg[1]);
         const float dz = (P[3 * j + 2] + mp[2]) - (G[3 * j + 2] + mg[2]);
-        pdist += sqrtf(dx * dx + dy * dy + dz * dz);
+        pdist += fast_sqrt(dx * dx + dy * dy + dz * dz);
       }
     }
   }
@@ -486,7 +491,7 @@ eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_consta
 // Second kernel of the two-kernel scheme (valid_bilinear.py:61-70): per-action fp64 sums of the per-pose
 // results.  Reads 4 B (action) + 4 / 8 B (per-pose sums) per pose; every thread keeps private fp64
 // buckets in registers (NA <= 16: predicated adds, no atomics, no shuffles in the loop).
-constexpr int kRedThreads = 256;
+constexpr int kRedThreads = 512;
 constexpr int kRedNA = 16;
 template <bool DO_M, bool DO_P>
 __global__ void __launch_bounds__(kRedThreads) action_reduce_kernel(const EvalParams prm) {
@@ -495,17 +500,28 @@ __global__ void __launch_bounds__(kRedThreads) action_reduce_kernel(const EvalPa
 #pragma unroll
   for (int a = 0; a < kRedNA; ++a) { s[a] = 0.0; ps[a] = 0.0; c[a] = 0u; }
   const int64_t stride = int64_t(gridDim.x) * kRedThreads;
-  for (int64_t i = int64_t(blockIdx.x) * kRedThreads + threadIdx.x; i < prm.n; i += stride) {
-    int act = prm.action ? __ldcs(prm.action + i) : 0;
-    act = min(max(act, 0), prm.n_actions - 1);
-    const double d = DO_M ? double(__ldcs(prm.dist_out + i)) : 0.0;
-    const double pd = DO_P ? double(__ldcs(prm.pdist_out + i)) : 0.0;
+  constexpr int U = 4;   // four poses per thread in flight
+  for (int64_t i0 = int64_t(blockIdx.x) * kRedThreads + threadIdx.x; i0 < prm.n; i0 += U * stride) {
+    int act[U];
+    float d[U], pd[U];
 #pragma unroll
-    for (int a = 0; a < kRedNA; ++a) {
-      const bool m = act == a;
-      if (DO_M) s[a] += m ? d : 0.0;
-      if (DO_P) ps[a] += m ? pd : 0.0;
-      c[a] += m ? 1u : 0u;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = min(i0 + u * stride, prm.n - 1);   // clamped; out-of-range slots are discarded below
+      act[u] = prm.action ? __ldcs(prm.action + i) : 0;
+      d[u] = DO_M ? __ldcs(prm.dist_out + i) : 0.f;
+      pd[u] = DO_P ? __ldcs(prm.pdist_out + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int au = (i0 + u * stride < prm.n) ? min(max(act[u], 0), prm.n_actions - 1) : -1;
+      const double dd = double(d[u]), pdd = double(pd[u]);
+#pragma unroll
+      for (int a = 0; a < kRedNA; ++a) {
+        const bool m = au == a;
+        if (DO_M) s[a] += m ? dd : 0.0;
+        if (DO_P) ps[a] += m ? pdd : 0.0;
+        c[a] += m ? 1u : 0u;
+      }
     }
   }
   __shared__ double bs[kRedThreads / 32][kRedNA], bps[kRedThreads / 32][kRedNA];
@@ -549,7 +565,8 @@ static cudaError_t launch_eval_tma_t(const EvalParams& prm, const CUtensorMap& t
   eval_kernel_tma<DO_M, DO_P, ACC><<<grid, kEvalThreads, smem, stream>>>(tp, tg, prm);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || ACC) return e;
-  const int rgrid = int(std::max<int64_t>(1, std::min<int64_t>((prm.n + kRedThreads - 1) / kRedThreads, int64_t(sms) * 2)));
+  // one CTA per SM: the final 3 x 15 double atomics per CTA all hit the same 45 addresses
+  const int rgrid = int(std::max<int64_t>(1, std::min<int64_t>((prm.n + kRedThreads - 1) / kRedThreads, int64_t(sms))));
   action_reduce_kernel<DO_M, DO_P><<<rgrid, kRedThreads, 0, stream>>>(prm);
   return cudaGetLastError();
 }

@@ -220,10 +220,10 @@ struct MegaParams {
   const CtaTiles* cta_tiles;  // [num_phases][gridDim.x] (nullptr: every phase is strided)
   const void* tmaps;        // array of CUtensorMap (128 B each, 64 B aligned)
   const int32_t* sched;     // per-phase tile lists (see Phase::sched_off)
-  unsigned int* barrier;    // grid barrier counter (zeroed before launch)
+  unsigned int* barrier;    // grid barrier counter: monotonic across launches (never reset), see bar_base
   unsigned long long* phase_ns;  // [8 * (num_phases + 1)] globaltimer stamps written by block 0 (nullptr: off)
   int32_t num_phases;
-  int32_t pad;
+  uint32_t bar_base;        // value of *barrier when this launch starts (the host keeps count)
   Dyn dyn;
 };
 

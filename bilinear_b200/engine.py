@@ -60,17 +60,29 @@ class Engine:
         self.fwd_counter = 0
         self.pending_backward = None  # batch size of the forward whose activations sit in the workspace
         self.scalars = None
+        self.host_out = None          # pinned [loss, grad norm] of the *_host entry points
+        self._bns = None
+        self._plist = None
 
     # ------------------------------------------------------------------ flat buffers
     def _params(self):
-        return list(self.module.parameters())
+        # the 22 Parameter OBJECTS never change (only their .data is re-pointed): walk the module tree once
+        if self._plist is None:
+            self._plist = list(self.module.parameters())
+        return self._plist
 
-    def _is_flat(self):
+    def _is_flat(self, thorough=False):
         if self.flat_p is None:
             return False
-        off = 0
         base = self.flat_p.data_ptr()
-        for p in self._params():
+        params = self._params()
+        if not thorough:
+            # hot path: .to() / load_state_dict / a foreign optimizer re-point all parameters or none
+            last = params[-1]
+            return (params[0].data_ptr() == base and
+                    last.data_ptr() == base + 4 * (_lib.PARAM_NUMEL - last.numel()))
+        off = 0
+        for p in params:
             if p.data_ptr() != base + 4 * off or p.device != self.flat_p.device or p.dtype != torch.float32:
                 return False
             off += p.numel()
@@ -140,8 +152,11 @@ class Engine:
 
     # ------------------------------------------------------------------ plans
     def _bn_layers(self):
-        m = self.module
-        return [m.encode[1], m.bilinear[0][0][1], m.bilinear[0][1][1], m.bilinear[1][0][1], m.bilinear[1][1][1]]
+        if self._bns is None:
+            m = self.module
+            self._bns = [m.encode[1], m.bilinear[0][0][1], m.bilinear[0][1][1], m.bilinear[1][0][1],
+                         m.bilinear[1][1][1]]
+        return self._bns
 
     def plan(self, batch, kind):
         self.ensure_flat()
@@ -206,7 +221,9 @@ class Engine:
 
     def _train_args(self, x, y, p_out, B):
         t = TrainArgs()
-        t.x, t.y, t.p_out = x.data_ptr(), (y.data_ptr() if y is not None else None), (p_out.data_ptr() if p_out is not None else None)
+        t.x = x.data_ptr() if x is not None else None
+        t.y = y.data_ptr() if y is not None else None
+        t.p_out = p_out.data_ptr() if p_out is not None else None
         if self.masks is not None:
             m = self.masks
             if tuple(m.shape) != (5, B, 1024) or m.dtype != torch.uint8 or not m.is_cuda:
@@ -268,6 +285,54 @@ class Engine:
         if update:
             pl.weights_version = self.weights_version = self.weights_version + 1
         return self.scalars[0], self.scalars[1]
+
+    def train_step_host(self, x_host, y_host, adam, update=True):
+        """train_bilinear.py:62-88 with its transfers: x_host [B, 32] / y_host [B, 48] are CPU tensors
+        (pinned for asynchronous copies); copies in, the one-kernel step, and the copy of (loss, grad norm)
+        back to pinned host memory are enqueued by ONE library call; returns the two Python floats after
+        synchronising the stream (the reference reads loss.item() every step as well)."""
+        if x_host.is_cuda or y_host.is_cuda:
+            raise RuntimeError("train_step_host() takes CPU tensors; use train_step() for CUDA tensors")
+        if x_host.dim() != 2 or x_host.shape[1] != 32 or y_host.shape != (x_host.shape[0], 48):
+            raise RuntimeError("expected x [B, 32] and y [B, 48]")
+        if x_host.dtype != torch.float32 or y_host.dtype != torch.float32 or not x_host.is_contiguous() \
+                or not y_host.is_contiguous():
+            x_host, y_host = x_host.float().contiguous(), y_host.float().contiguous()
+        B = x_host.shape[0]
+        if B < 2:
+            raise ValueError("Expected more than 1 value per channel when training, got input size %s"
+                             % str(torch.Size([B, 1024])))
+        pl = self.plan(B, PLAN_TRAIN)
+        if self.host_out is None:
+            self.host_out = torch.zeros(2, dtype=torch.float32).pin_memory()
+        t = self._train_args(None, None, None, B)
+        stream = torch.cuda.current_stream()
+        check(_lib.lib().b200_train_step_host(pl.handle, C.c_void_p(x_host.data_ptr()), C.c_void_p(y_host.data_ptr()),
+                                              C.byref(t), C.byref(adam), 1 if update else 0,
+                                              C.c_void_p(self.host_out.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        self.fwd_counter += 1
+        self.pending_backward = None
+        if update:
+            pl.weights_version = self.weights_version = self.weights_version + 1
+        stream.synchronize()
+        return float(self.host_out[0]), float(self.host_out[1])
+
+    def forward_eval_host(self, x_host, out_host=None):
+        """valid_bilinear.py:39-52 with its transfers: CPU x [B, 32] -> CPU prediction [B, 48] (pinned)."""
+        if x_host.is_cuda:
+            raise RuntimeError("forward_eval_host() takes a CPU tensor")
+        x_host = x_host.float().contiguous()
+        B = x_host.shape[0]
+        self.ensure_flat()
+        kind = PLAN_TRAIN if (B, PRECISIONS[self.module.precision], PLAN_TRAIN) in {k[:3] for k in self.plans} else PLAN_INFER
+        pl = self.plan(B, kind)
+        if out_host is None:
+            out_host = torch.empty(B, 48, dtype=torch.float32).pin_memory()
+        stream = torch.cuda.current_stream()
+        check(_lib.lib().b200_forward_eval_host(pl.handle, C.c_void_p(x_host.data_ptr()),
+                                                C.c_void_p(out_host.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        stream.synchronize()
+        return out_host
 
     def adam_step(self, adam, batch_hint=None):
         """clip_grad_norm_ + Adam.step on the flat gradient buffer (train_bilinear.py:81-83)."""

@@ -116,6 +116,20 @@ class BilinearUnit(nn.Module):
         return optimizer.fused_step(self, in_image_space, in_camera_space, max_norm, update, grad_scale)
 
 
+def _train_step_host(self, optimizer, in_image_space, in_camera_space, max_norm=1.0, update=True, grad_scale=1.0):
+    """The body of the loop train_bilinear.py:62-88 INCLUDING its transfers, for CPU (pinned) batches as a
+    DataLoader(pin_memory=True) delivers them: host->device copies, the one-kernel training iteration and
+    the loss read-back are one library call.  Returns (loss, grad_norm) as Python floats."""
+    if not self.training:
+        raise RuntimeError("train_step_host() needs the module in training mode")
+    if not next(self.parameters()).is_cuda:
+        raise RuntimeError("bilinear_b200 runs on CUDA (sm_100a) only: move the module to a CUDA device")
+    return optimizer.fused_step_host(self, in_image_space, in_camera_space, max_norm, update, grad_scale)
+
+
+BilinearUnit.train_step_host = _train_step_host
+
+
 def _latest_epoch(parameter_dir):
     """Largest N among the '{N}.save' files below parameter_dir (0: none).  Like the reference
     (model/bilinear.py:63-72) any file whose name is not '<int>.<ext>' raises ValueError."""

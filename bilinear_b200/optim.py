@@ -61,6 +61,18 @@ class FusedAdam(torch.optim.Adam):
             self._adopt_state()
         return out
 
+    def fused_step_host(self, module, x_host, y_host, max_norm=1.0, update=True, grad_scale=1.0):
+        assert module is self._module
+        eng = get_engine(module)
+        lr, betas, eps = self._hyper()
+        if update:
+            self._t += 1
+        out = eng.train_step_host(x_host, y_host, eng.adam_args(lr, max(self._t, 1), max_norm, grad_scale, betas, eps),
+                                  update=update)
+        if update and not self.state:
+            self._adopt_state()
+        return out
+
     def finish_step(self, max_norm=1.0, grad_scale=1.0):
         """Data parallel: clip + Adam on the (already all-reduced) flat gradient buffer."""
         eng = get_engine(self._module)

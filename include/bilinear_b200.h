@@ -120,6 +120,19 @@ int b200_backward(b200_plan* plan, const float* dP, void* stream);
 int b200_train_step(b200_plan* plan, const b200_train_args* targs, const b200_adam_args* aargs, int32_t update,
                     void* stream);
 
+/* The same iteration fed from HOST memory, i.e. the body of the loop train_bilinear.py:62-88 including its
+ * transfers: x_host [B][32] and y_host [B][48] (pinned memory for truly asynchronous copies) are copied to
+ * staging buffers inside the workspace (train_bilinear.py:72-73), the step runs as one kernel, and the mean
+ * loss and the pre-clip gradient norm are copied back to out_host[0], out_host[1] (train_bilinear.py:86-88).
+ * targs->x / y / loss_out / gnorm_out are ignored.  Asynchronous: synchronise `stream` before reading
+ * out_host. */
+int b200_train_step_host(b200_plan* plan, const float* x_host, const float* y_host, const b200_train_args* targs,
+                         const b200_adam_args* aargs, int32_t update, float* out_host, void* stream);
+
+/* Eval-mode forward fed from / returning to HOST memory (valid_bilinear.py:39-52 with its transfers):
+ * x_host [B][32] -> p_host [B][48].  Asynchronous like b200_train_step_host. */
+int b200_forward_eval_host(b200_plan* plan, const float* x_host, float* p_host, void* stream);
+
 /* clip_grad_norm_ + Adam.step on whatever is in `grads` (train_bilinear.py:81-83). */
 int b200_adam_step(b200_plan* plan, const b200_adam_args* aargs, float* gnorm_out, void* stream);
 

@@ -353,6 +353,46 @@ def test_fused_train_step(cuda_lib, precision, batch):
     assert float(opt.state_dict()["state"][0]["step"]) == 4.0
 
 
+@pytest.mark.parametrize("precision,batch", [("fp32", 64), ("bf16", 1000)])
+def test_host_buffer_step_equals_device_step(cuda_lib, precision, batch):
+    """b200_train_step_host (pinned host batches in, loss / gradient norm out) is the same iteration as
+    b200_train_step on device tensors: identical parameters, moments and scalars."""
+    x, y, masks = bo.synthetic_batch(23, batch)
+    outs = []
+    for host in (False, True):
+        net, opt = make_net(2, precision)
+        net.train()
+        net.inject_dropout_masks(masks_tensor(masks))
+        if host:
+            loss, gnorm = net.train_step_host(opt, x.pin_memory(), y.pin_memory(), max_norm=1.0)
+        else:
+            loss, gnorm = net.train_step(opt, x.cuda(), y.cuda(), max_norm=1.0)
+            loss, gnorm = float(loss), float(gnorm)
+        torch.cuda.synchronize()
+        outs.append((loss, gnorm, [p.detach().clone() for p in net.parameters()],
+                     {k: v.clone() for k, v in net.state_dict().items() if "running" in k}))
+    tol = 1e-6 if precision == "fp32" else 1e-4   # split-K wgrad reductions add in a run-dependent order
+    assert abs(outs[0][0] - outs[1][0]) <= tol * abs(outs[0][0])
+    assert abs(outs[0][1] - outs[1][1]) <= tol * abs(outs[0][1])
+    for a, b in zip(outs[0][2], outs[1][2]):
+        assert float((a - b).abs().max()) <= 1e-6
+    for k in outs[0][3]:
+        assert torch.equal(outs[0][3][k], outs[1][3][k]), k
+    with pytest.raises(RuntimeError):
+        net.train_step_host(opt, x.cuda(), y.cuda())
+
+
+def test_eval_host_buffers(cuda_lib):
+    net, _ = make_net(3, "fp32")
+    net.eval()
+    x = torch.randn(257, 32)
+    from bilinear_b200.engine import get_engine
+    p_host = get_engine(net).forward_eval_host(x.pin_memory())
+    with torch.no_grad():
+        p_dev = net(x.cuda())
+    assert torch.equal(p_host, p_dev.cpu())
+
+
 def test_fused_multi_step_trajectory(cuda_lib):
     """Five consecutive fused steps (weights refreshed in-kernel) track the oracle; then eval."""
     st = bo.State(reference_init_state(1), dtype=torch.float64)
