@@ -1007,6 +1007,7 @@ int b200_debug_phase_ns(b200_plan* plan, int64_t* ns_out, int32_t* kinds_out, in
     // producer done, MMA issue done, first accumulator ready, epilogue done, work done (block 0), spare
     ns_out[8 * i] = int64_t(t[8 * (i + 1)] - t[8 * i]);
     for (int k = 1; k < 8; ++k) ns_out[8 * i + k] = t[8 * i + k] >= t[8 * i] ? int64_t(t[8 * i + k] - t[8 * i]) : -1;
+    if (i == 0) ns_out[7] = int64_t(t[0] - t[7]);   // kernel entry -> start of the first phase
     const PhaseBlob& bl = plan->blobs[plan->last_first + i];
     const Phase& ph = bl.ph;
     if (kinds_out) kinds_out[i] = ph.gemm_tiles > 0 ? 0 : 1 + bl.ej[0].kind;

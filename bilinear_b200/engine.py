@@ -358,7 +358,7 @@ class Engine:
         tiles = (C.c_int32 * n)()
         cnt = C.c_int32(0)
         check(_lib.lib().b200_debug_phase_ns(pl.handle, ns, kinds, tiles, n, C.byref(cnt)))
-        return [(int(ns[8 * i]), int(kinds[i]), int(tiles[i]), [int(ns[8 * i + k]) for k in range(1, 7)])
+        return [(int(ns[8 * i]), int(kinds[i]), int(tiles[i]), [int(ns[8 * i + k]) for k in range(1, 8)])
                 for i in range(cnt.value)]
 
     def debug_keep_bits(self, layer, batch):

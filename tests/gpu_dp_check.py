@@ -1,0 +1,91 @@
+"""Data-parallel training step on N GPUs against the oracle (not a pytest module; launched by torchrun):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+        tests/gpu_dp_check.py
+
+Every rank takes its rows of one global batch, runs the one-kernel step without the optimizer phase, the flat
+gradient is all-reduced over NCCL, and clip + Adam run on the average.  Oracle: "reference per shard (local
+BatchNorm), gradients averaged, clip + Adam on the average" (SURVEY.md section 8(e)(i))."""
+import os
+import sys
+import warnings
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import torch.distributed as dist
+
+from bilinear_b200 import parallel
+from bilinear_b200.engine import get_engine
+from bilinear_b200.model import bilinear as mb
+from oracle import bilinear_oracle as bo
+
+
+def main():
+    rank, local_rank, world = parallel.init()
+    dev = torch.device("cuda", local_rank)
+    per = 64
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net, opt, step, _ = mb.load(torch.device("cpu"))
+    st = bo.State({k: v.clone() for k, v in net.state_dict().items()}, dtype=torch.float64)
+    net.to(dev)
+    net.train()
+    x, y, masks = bo.synthetic_batch(77, per * world)
+    lo, hi = rank * per, (rank + 1) * per
+    net.inject_dropout_masks(torch.stack([m[lo:hi] for m in masks]).to(dev))
+    lr = bo.lr_schedule(1)
+    for g in opt.param_groups:
+        g["lr"] = lr
+    loss, _ = net.train_step(opt, x[lo:hi].to(dev), y[lo:hi].to(dev), max_norm=1.0, update=False)
+    parallel.allreduce_gradients(get_engine(net).flat_g)
+    gnorm = opt.finish_step(max_norm=1.0, grad_scale=1.0 / world)
+    torch.cuda.synchronize()
+
+    # oracle: every shard separately (local BatchNorm), gradients averaged
+    grads_sum = None
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_net, _, _, _ = mb.load(torch.device("cpu"))
+    init_sd = {k: v.clone() for k, v in ref_net.state_dict().items()}
+    for r in range(world):
+        a, b = r * per, (r + 1) * per
+        s_r = bo.State({k: v.clone() for k, v in init_sd.items()}, dtype=torch.float64)
+        p, cache = bo.forward(s_r, x[a:b].double(), train=True, masks=[m[a:b] for m in masks])
+        l, dP = bo.mse_loss(p, y[a:b].double())
+        if r == rank:
+            my_loss = float(l)
+        g = bo.backward(s_r, cache, dP)
+        grads_sum = g if grads_sum is None else {k: grads_sum[k] + g[k] for k in g}
+    s0 = bo.State({k: v.clone() for k, v in init_sd.items()}, dtype=torch.float64)
+    norm_ref = bo.clip_and_adam(s0, grads_sum, lr, max_norm=1.0, grad_scale=1.0 / world)
+
+    ok = abs(float(loss) - my_loss) < 1e-5 * my_loss
+    ok = ok and abs(float(gnorm) - float(norm_ref)) < 1e-5 * float(norm_ref)
+    worst = 0.0
+    for name, prm in net.named_parameters():
+        d_gpu = prm.detach().double().cpu() - init_sd[name].double()
+        d_ref = s0.p[name] - init_sd[name].double()
+        if name.endswith(".0.bias") and not name.startswith("decode"):
+            continue    # analytically zero gradient (SURVEY.md hard part 3)
+        e = float((d_gpu - d_ref).norm() / (d_ref.norm() + 1e-30))
+        worst = max(worst, e)
+    ok = ok and worst < 1e-3
+    # all ranks must hold identical parameters after the step
+    flat = get_engine(net).flat_p.clone()
+    ref = flat.clone()
+    dist.broadcast(ref, 0)
+    same = bool(torch.equal(flat, ref))
+    print("rank %d: loss %.6f (oracle %.6f) |g| %.6f (oracle %.6f) worst rel update err %.2e identical-params %s -> %s"
+          % (rank, float(loss), my_loss, float(gnorm), float(norm_ref), worst, same, "OK" if (ok and same) else "FAIL"),
+          flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if (ok and same) else 1)
+
+
+if __name__ == "__main__":
+    main()

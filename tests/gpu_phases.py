@@ -24,7 +24,9 @@ def show(tag, ph):
         else:
             name = "EW   %-12s jobs=%d" % (EW[kind - 1], tiles)
         print("   %2d %-34s %9.1f us   [prod0 %s prodEnd %s mmaEnd %s acc0 %s epiEnd %s work %s]" %
-              ((i, name, ns / 1e3) + tuple("%.1f" % (s / 1e3) if s >= 0 else "-" for s in sub)))
+              ((i, name, ns / 1e3) + tuple("%.1f" % (s / 1e3) if s >= 0 else "-" for s in sub[:6])))
+        if i == 0 and len(sub) > 6:
+            print("      (kernel entry -> first phase: %.1f us)" % (sub[6] / 1e3))
     sys.stdout.flush()
 
 
@@ -44,6 +46,13 @@ def main():
         for _ in range(3):
             net.train_step(opt, x, y)
         torch.cuda.synchronize()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(21)]
+        evs[0].record()
+        for k in range(20):
+            net.train_step(opt, x, y)
+            evs[k + 1].record()
+        torch.cuda.synchronize()
+        print("   back-to-back steps, event-timed: %s us" % " ".join("%.0f" % (evs[k].elapsed_time(evs[k + 1]) * 1e3) for k in range(20)))
         eng = get_engine(net)
         show("train_step %s B=%d" % (prec, b), eng.debug_phase_ns(b))
         net.eval()
