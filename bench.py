@@ -126,6 +126,9 @@ class TrainLoop:
         self.torch, self.parallel = torch, parallel
         self.net, self.opt, self.step = make_model(precision, device)
         self.batch, self.world, self.device = batch, world, device
+        self.fused_dp = world > 1 and os.environ.get("BILINEAR_B200_DP", "fused") == "fused"
+        if self.fused_dp:
+            self.net.enable_data_parallel()
         g = torch.Generator(device="cpu").manual_seed(1234 + parallel.env_world()[0])
         self.xs = [torch.randn(batch, 32, generator=g).to(device) for _ in range(nbatches)]
         self.ys = [torch.randn(batch, 48, generator=g).to(device) for _ in range(nbatches)]
@@ -145,6 +148,8 @@ class TrainLoop:
         self.i += 1
         if self.world == 1:
             out = self.net.train_step(self.opt, x, y, max_norm=1.0)
+        elif self.fused_dp:
+            out = self.net.train_step_dp(self.opt, x, y, max_norm=1.0)
         else:
             from bilinear_b200.engine import get_engine
             out = self.net.train_step(self.opt, x, y, max_norm=1.0, update=False)
@@ -458,7 +463,9 @@ def main():
             "config": {"workload": "%s: batch %d per GPU, 16 joints, 1024 hidden, 2 residual blocks, random init, "
                                    "Philox dropout, clip_grad_norm 1, Adam" % (args.workload, batch),
                        "batch_per_gpu": batch, "global_batch": batch * world,
-                       "parallelism": "dp%d (local BatchNorm, NCCL all-reduce of the flat gradient)" % world
+                       "parallelism": ("dp%d (local BatchNorm, gradient all-reduce inside the persistent kernel over "
+                                       "NVLink peer memory)" if os.environ.get("BILINEAR_B200_DP", "fused") == "fused" else
+                                       "dp%d (local BatchNorm, NCCL all-reduce of the flat gradient)") % world
                        if world > 1 else "single GPU",
                        "l2": "flushed (256 MB fill) between timed iterations" if batch <= 4096 else
                              "activations exceed L2"},

@@ -46,6 +46,11 @@ class TrainArgs(C.Structure):
     ]
 
 
+class CommDesc(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32), ("reserved", C.c_uint32),
+                ("buffers", C.c_void_p * 8)]
+
+
 _SIGS = {
     "b200_version": (C.c_int, []),
     "b200_last_error": (C.c_char_p, []),
@@ -62,6 +67,14 @@ _SIGS = {
     "b200_train_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TrainArgs), C.POINTER(AdamArgs),
                                        C.c_int32, C.c_void_p, C.c_void_p]),
     "b200_forward_eval_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200_comm_bytes": (C.c_int64, []),
+    "b200_comm_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "b200_comm_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200_comm_close": (C.c_int, [C.c_void_p]),
+    "b200_comm_free": (C.c_int, [C.c_void_p]),
+    "b200_plan_set_comm": (C.c_int, [C.c_void_p, C.POINTER(CommDesc)]),
+    "b200_train_step_dp": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.POINTER(AdamArgs), C.POINTER(C.c_uint32),
+                                     C.c_void_p]),
     "b200_adam_step": (C.c_int, [C.c_void_p, C.POINTER(AdamArgs), C.c_void_p, C.c_void_p]),
     "b200_mpjpe": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 4),
     "b200_pmpjpe": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 4),

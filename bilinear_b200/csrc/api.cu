@@ -137,7 +137,7 @@ constexpr int kSmallSplit = 16;      // K slices of the small-batch GEMMs (K = 1
 struct Bufs {
   CUtensorMap* tmaps; PhaseBlob* blobs; CtaTiles* cta_tiles; unsigned int* barrier;
   unsigned long long* phase_ns;
-  int32_t* sched; AdamTab* adam_tab; FoldTab* fold_tab;
+  int32_t* sched; AdamTab* adam_tab; FoldTab* fold_tab; CommTab* comm_tab;
   uint16_t* wplanes; int64_t wplane_stride;   // bf16 planes of the whole flat parameter buffer
   float* part;                       // small path: [kSmallSplit][1024][Bs] fp32 partial sums
   float* x_save;                     // small path: copy of the input batch [Bs][32] fp32
@@ -178,6 +178,7 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
   u.sched = c.take_n<int32_t>(kMaxSched);
   u.adam_tab = c.take_n<AdamTab>(1);
   u.fold_tab = c.take_n<FoldTab>(1);
+  u.comm_tab = c.take_n<CommTab>(1);
   u.part = large ? nullptr : c.take_n<float>(int64_t(kSmallSplit) * kHidden * Bs);
   u.x_save = large ? nullptr : c.take_n<float>(Bs * kDin);
   u.x_stage = c.take_n<float>(Bs * kDin);
@@ -250,7 +251,9 @@ struct b200_plan {
   std::vector<PhaseBlob> blobs;
   std::vector<CtaTiles> cta_tiles;   // [phase][sms]
   std::vector<int32_t> sched;
-  Sched s_refresh, s_eval, s_fwd, s_bwd, s_step, s_update;
+  Sched s_refresh, s_eval, s_fwd, s_bwd, s_step, s_update, s_step_dp;
+  bool has_comm = false;
+  uint32_t comm_epoch = 1;   // flag value of the next cross-GPU barrier (flags start at 0)
   PhaseBlob cur;
   uint32_t bar_count = 0;   // grid-barrier arrivals so far (device counter is monotonic)
   int last_first = 0, last_count = 0;
@@ -734,6 +737,31 @@ static int build_plan(b200_plan* pl) {
   }
   if (end_phase(pl)) return 1;
   pl->s_update.count = int(pl->blobs.size()) - pl->s_update.first;
+
+  // ---- fused DATA-PARALLEL step: forward, backward, in-kernel all-reduce of the flat gradient over NVLink
+  // peer memory, clip + Adam on the sum (x 1/world) -- one persistent kernel per rank and iteration
+  pl->s_step_dp.first = int(pl->blobs.size());
+  if (prep_fwd(true)) return 1;
+  for (int l = 0; l < kNumHeavy; ++l)
+    if (build_fwd_layer(pl, l, true, l == 0 && !pl->large)) return 1;
+  if (build_decode(pl, true, true)) return 1;
+  if (build_backward(pl, false, nullptr, 0)) return 1;      // the clipping norm is taken on the REDUCED gradient
+  for (int k = 0; k < 3; ++k) {
+    Args a = base_args(pl, 0);
+    a.comm = u.comm_tab;
+    a.comm_step = (k == 2) ? 1 : 0;
+    begin_phase(pl);
+    if (add_ew(pl, k == 1 ? EW_ALLREDUCE : EW_COMM_BARRIER, a)) return 1;
+    if (end_phase(pl)) return 1;
+  }
+  begin_phase(pl);
+  {
+    Args a = adam_args(pl);
+    a.comm = u.comm_tab;
+    if (add_ew(pl, EW_ADAM, a)) return 1;
+  }
+  if (end_phase(pl)) return 1;
+  pl->s_step_dp.count = int(pl->blobs.size()) - pl->s_step_dp.first;
   return 0;
 }
 
@@ -885,6 +913,73 @@ int b200_train_step(b200_plan* plan, const b200_train_args* targs, const b200_ad
   int rc = run_sched(plan, plan->s_step, count, d, (cudaStream_t)stream);
   if (rc) return rc;
   return 0;
+}
+
+// ---- data parallel over NVLink peer memory --------------------------------------------------------
+int b200_comm_alloc(int64_t bytes, void** dev_ptr, void* handle64) {
+  if (!dev_ptr || !handle64 || bytes <= 0) return fail("bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  CK(cudaMalloc(&p, size_t(bytes)));
+  CK(cudaMemset(p, 0, size_t(bytes)));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return fail("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return 0;
+}
+int b200_comm_open(const void* handle64, void** peer_ptr) {
+  if (!handle64 || !peer_ptr) return fail("null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CK(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int b200_comm_close(void* peer_ptr) {
+  if (peer_ptr) CK(cudaIpcCloseMemHandle(peer_ptr));
+  return 0;
+}
+int b200_comm_free(void* dev_ptr) {
+  if (dev_ptr) CK(cudaFree(dev_ptr));
+  return 0;
+}
+int64_t b200_comm_bytes(void) { return int64_t(kPL.numel) * 4 + int64_t(sizeof(CommCtl)); }
+
+int b200_plan_set_comm(b200_plan* plan, const b200_comm_desc* c) {
+  if (!plan || !c) return fail("null argument");
+  if (c->world < 1 || c->world > kMaxRanks || c->rank < 0 || c->rank >= c->world) return fail("bad rank / world size");
+  if (plan->kind != B200_PLAN_TRAIN) return fail("training plan required");
+  if (c->buffers[c->rank] != (void*)plan->d.grads)
+    return fail("the plan's gradient buffer must be this rank's communication buffer");
+  CommTab t;
+  memset(&t, 0, sizeof t);
+  for (int r = 0; r < c->world; ++r) {
+    if (!c->buffers[r]) return fail("missing peer buffer");
+    t.grads[r] = reinterpret_cast<float*>(c->buffers[r]);
+    t.ctl[r] = reinterpret_cast<CommCtl*>(reinterpret_cast<uint8_t*>(c->buffers[r]) + int64_t(kPL.numel) * 4);
+  }
+  t.rank = c->rank; t.world = c->world; t.numel = kPL.numel;
+  t.sq_local = plan->u.loss_acc + 12;
+  CK(cudaMemcpy(plan->u.comm_tab, &t, sizeof t, cudaMemcpyHostToDevice));
+  plan->has_comm = true;
+  plan->comm_epoch = c->epoch ? c->epoch : 1;
+  return 0;
+}
+
+int b200_train_step_dp(b200_plan* plan, const b200_train_args* targs, const b200_adam_args* aargs, uint32_t* epoch_io,
+                       void* stream) {
+  if (!plan || !targs || !targs->x || !targs->y || !aargs) return fail("null argument");
+  if (!plan->has_comm) return fail("b200_plan_set_comm has not been called on this plan");
+  if (!plan->d.exp_avg || !plan->d.exp_avg_sq) return fail("optimizer state missing");
+  if (plan->B < 2) return fail("Expected more than 1 value per channel when training, got input size [1, 1024]");
+  Dyn d = make_dyn(targs, aargs);
+  // the flags are shared by all plans of this process: the caller carries the epoch across plans
+  if (epoch_io && *epoch_io) plan->comm_epoch = *epoch_io;
+  d.comm_epoch = plan->comm_epoch;
+  plan->comm_epoch += 2;
+  if (epoch_io) *epoch_io = plan->comm_epoch;
+  return run_sched(plan, plan->s_step_dp, plan->s_step_dp.count, d, (cudaStream_t)stream);
 }
 
 int b200_train_step_host(b200_plan* plan, const float* x_host, const float* y_host, const b200_train_args* targs,

@@ -53,6 +53,8 @@ enum EwKind : int32_t {
   EW_BN_FWD_SMALL = 9, // small path: sum K-slice partials -> bias, BN (batch or running stats), ReLU, dropout, skip
   EW_BN_BWD_SMALL = 10,// small path: sum partials (+skip grad) -> dropout/ReLU/BN backward -> dz, dgamma, dbeta, db
   EW_DECODE_SMALL = 11,// small path: sum partials + bias -> p; optional MSE loss, dP planes, decode bias grad
+  EW_COMM_BARRIER = 12,// data parallel: cross-GPU barrier through flags in peer memory (block 0 only)
+  EW_ALLREDUCE = 13,   // data parallel: reduce-scatter + all-gather of the flat gradient over NVLink peer memory
 };
 
 // bf16 "plane" tensor: value = sum_p plane[p].  planes = 1 (bf16 mode) or 3 (fp32-parity mode:
@@ -78,6 +80,7 @@ struct Dyn {
   float max_norm;          // clip_grad_norm_ max_norm (<= 0: no clipping)
   float grad_scale;        // 1 / world_size under data parallel
   float momentum[kNumHeavy];  // >= 0: BN momentum; < 0: cumulative average (momentum=None)
+  uint32_t comm_epoch;     // data parallel: flag value of the first cross-GPU barrier of this launch
 };
 
 enum DynSrc : int32_t { SRC_NONE = 0, SRC_X = 1, SRC_DP = 2 };
@@ -93,6 +96,24 @@ struct alignas(16) FoldTab {
   const float* run_var[kNumHeavy];
   float* scale[kNumHeavy];
   float* shift[kNumHeavy];
+};
+
+// Data-parallel exchange over NVLink / NVSwitch peer memory (one per plan, in device memory; the
+// EW_COMM_BARRIER / EW_ALLREDUCE jobs and the Adam phase reach it through Args::comm).  Every rank maps
+// every other rank's flat gradient buffer and control block (CUDA IPC); rank r owns slice r of the
+// buffer: it sums that slice over all ranks and writes the sum back into every rank's buffer.
+constexpr int kMaxRanks = 8;
+struct CommCtl {                 // lives at the end of each rank's communication buffer
+  uint32_t flag[kMaxRanks];      // flag[r] is written by rank r (release.sys) and polled by the owner
+  uint32_t pad[8];
+  double sq[kMaxRanks];          // sq[r]: sum of squares of the reduced slice r, written by rank r
+};
+struct alignas(16) CommTab {
+  float* grads[kMaxRanks];       // peer-mapped flat gradient buffers, index = rank
+  CommCtl* ctl[kMaxRanks];
+  int32_t rank, world;
+  int64_t numel;
+  double* sq_local;              // this rank's accumulator for its slice (cleared at the start of a step)
 };
 
 // Adam / weight-plane table (one per plan, in device memory; referenced by EW_ADAM / EW_SPLIT_W /
@@ -165,6 +186,9 @@ struct alignas(16) Args {
   float* grad_w0;          // EW_BN_BWD_SMALL of the first layer: dW0 [1024][32] (nullptr: no fused wgrad)
   const AdamTab* adam;     // EW_ADAM / EW_SPLIT_W / EW_SUMSQ
   const FoldTab* fold;     // EW_BN_FOLD
+  const CommTab* comm;     // EW_COMM_BARRIER / EW_ALLREDUCE; EW_ADAM: clip norm from the exchanged slice sums
+  int32_t comm_step;       // EW_COMM_BARRIER: 0 = before the exchange, 1 = after it (publishes the slice sum)
+  int32_t pad_c;
 };
 
 struct alignas(16) GemmJob {

@@ -63,6 +63,7 @@ class Engine:
         self.host_out = None          # pinned [loss, grad norm] of the *_host entry points
         self._bns = None
         self._plist = None
+        self.comm = None              # parallel.PeerComm: in-kernel data-parallel gradient exchange
 
     # ------------------------------------------------------------------ flat buffers
     def _params(self):
@@ -99,7 +100,13 @@ class Engine:
         n = sum(p.numel() for p in params)
         assert n == _lib.PARAM_NUMEL, n
         flat_p = torch.empty(n, dtype=torch.float32, device=dev)
-        flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        if self.comm is not None:
+            if self.comm.device != dev:
+                raise RuntimeError("the gradient exchange buffers live on %s, the module on %s" % (self.comm.device, dev))
+            flat_g = self.comm.grads          # gradients are written straight into the peer-mapped buffer
+            flat_g.zero_()
+        else:
+            flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
         with torch.no_grad():
             for p in params:
@@ -117,6 +124,12 @@ class Engine:
         self.scalars = torch.zeros(8, dtype=torch.float32, device=dev)
         self.weights_version += 1
         self._seen_torch_version = self._torch_versions()
+
+    def attach_comm(self, comm):
+        """Data parallel: from now on the flat gradient buffer is `comm`'s peer-mapped buffer."""
+        self.comm = comm
+        self.flat_p = None            # re-flatten (and rebuild the plans) on the next call
+        self.plans.clear()
 
     def grad_views(self):
         out, off = [], 0
@@ -189,6 +202,9 @@ class Engine:
             h = C.c_void_p()
             check(L.b200_plan_create(C.byref(d), C.byref(h)))
             pl = _Plan(h, ws, batch, precision, kind)
+            if self.comm is not None and kind == PLAN_TRAIN:
+                cd = self.comm.desc()
+                check(L.b200_plan_set_comm(h, C.byref(cd)))
             if len(self.plans) > 8:      # ragged tail batches come and go; keep the cache bounded
                 self.plans.pop(next(iter(self.plans)))
             self.plans[key] = pl
@@ -284,6 +300,29 @@ class Engine:
         self.pending_backward = None
         if update:
             pl.weights_version = self.weights_version = self.weights_version + 1
+        return self.scalars[0], self.scalars[1]
+
+    def train_step_dp(self, x, y, adam):
+        """Data-parallel iteration as ONE kernel per rank: forward, backward, all-reduce of the flat gradient
+        over NVLink peer memory, clip + Adam on the average.  Every rank must call it for the same step."""
+        if self.comm is None:
+            raise RuntimeError("attach_comm(parallel.PeerComm(...)) first")
+        x = self._check_input(x, 32)
+        y = self._check_input(y, 48)
+        B = x.shape[0]
+        if B < 2:
+            raise ValueError("Expected more than 1 value per channel when training, got input size %s"
+                             % str(torch.Size([B, 1024])))
+        pl = self.plan(B, PLAN_TRAIN)
+        t = self._train_args(x, y, None, B)
+        t.loss_out = self.scalars[0:1].data_ptr()
+        t.gnorm_out = self.scalars[1:2].data_ptr()
+        ep = C.c_uint32(self.comm.epoch)
+        check(_lib.lib().b200_train_step_dp(pl.handle, C.byref(t), C.byref(adam), C.byref(ep), _stream()))
+        self.comm.epoch = ep.value
+        self.fwd_counter += 1
+        self.pending_backward = None
+        pl.weights_version = self.weights_version = self.weights_version + 1
         return self.scalars[0], self.scalars[1]
 
     def train_step_host(self, x_host, y_host, adam, update=True):

@@ -116,6 +116,31 @@ class BilinearUnit(nn.Module):
         return optimizer.fused_step(self, in_image_space, in_camera_space, max_norm, update, grad_scale)
 
 
+def _train_step_dp(self, optimizer, in_image_space, in_camera_space, max_norm=1.0):
+    """Data-parallel variant of train_step(): this rank's rows of the global batch in, gradients averaged over
+    all ranks INSIDE the kernel (NVLink peer memory), identical parameters on every rank out.  Needs
+    `bilinear_b200.parallel.PeerComm` attached (see enable_data_parallel)."""
+    if not self.training:
+        raise RuntimeError("train_step_dp() needs the module in training mode")
+    eng = get_engine(self)
+    return optimizer.fused_step_dp(self, in_image_space, in_camera_space, max_norm, eng.comm.world)
+
+
+def _enable_data_parallel(self, group=None):
+    """Allocate and exchange the peer-mapped gradient buffers (once, after .to(device))."""
+    from .. import parallel
+    eng = get_engine(self)
+    dev = next(self.parameters()).device
+    if not dev.type == "cuda":
+        raise RuntimeError("bilinear_b200 runs on CUDA (sm_100a) only: move the module to a CUDA device first")
+    eng.attach_comm(parallel.PeerComm(dev, group))
+    return self
+
+
+BilinearUnit.train_step_dp = _train_step_dp
+BilinearUnit.enable_data_parallel = _enable_data_parallel
+
+
 def _train_step_host(self, optimizer, in_image_space, in_camera_space, max_norm=1.0, update=True, grad_scale=1.0):
     """The body of the loop train_bilinear.py:62-88 INCLUDING its transfers, for CPU (pinned) batches as a
     DataLoader(pin_memory=True) delivers them: host->device copies, the one-kernel training iteration and

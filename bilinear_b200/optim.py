@@ -61,6 +61,16 @@ class FusedAdam(torch.optim.Adam):
             self._adopt_state()
         return out
 
+    def fused_step_dp(self, module, x, y, max_norm=1.0, world=1):
+        assert module is self._module
+        eng = get_engine(module)
+        lr, betas, eps = self._hyper()
+        self._t += 1
+        out = eng.train_step_dp(x, y, eng.adam_args(lr, self._t, max_norm, 1.0 / world, betas, eps))
+        if not self.state:
+            self._adopt_state()
+        return out
+
     def fused_step_host(self, module, x_host, y_host, max_norm=1.0, update=True, grad_scale=1.0):
         assert module is self._module
         eng = get_engine(module)

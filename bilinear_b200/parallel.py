@@ -73,6 +73,75 @@ def allreduce_gradients(flat_g, group=None, bucketed=True):
     return flat_g
 
 
+class _RawCuda:
+    """Minimal __cuda_array_interface__ carrier: lets torch view memory the library allocated."""
+
+    def __init__(self, ptr, numel):
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerComm:
+    """Gradient exchange buffers for the IN-KERNEL all-reduce (csrc/mega.cu: ew_allreduce): every rank
+    cudaMalloc's its flat gradient buffer (+ control block) through the library, the 64-byte CUDA IPC handles
+    travel through one torch.distributed all_gather, and every rank maps every peer's buffer.  torch only
+    carries the handles; the data path is NVLink loads / stores issued by the persistent kernel."""
+
+    def __init__(self, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self._C, self._L = C, _lib.lib()
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.world > 8:
+            raise RuntimeError("the in-kernel gradient exchange supports up to 8 ranks (one NVSwitch domain)")
+        self.device = torch.device(device)
+        nbytes = self._L.b200_comm_bytes()
+        own = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.b200_comm_alloc(nbytes, C.byref(own), handle))
+        self.own = own.value
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        if self.world > 1:
+            allh = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            allh = allh.cpu().view(self.world, 64)
+        else:
+            allh = mine.cpu().view(1, 64)
+        self.ptrs, self._opened = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                self.ptrs.append(self.own)
+                continue
+            hb = (C.c_uint8 * 64)(*[int(v) for v in allh[r]])
+            p = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.b200_comm_open(hb, C.byref(p)))
+            self.ptrs.append(p.value)
+            self._opened.append(p.value)
+        self.grads = torch.as_tensor(_RawCuda(self.own, _lib.PARAM_NUMEL), device=self.device)
+        self.epoch = 1
+        barrier()
+
+    def desc(self):
+        from ._lib import CommDesc
+        d = CommDesc()
+        d.rank, d.world, d.epoch = self.rank, self.world, self.epoch
+        for r, p in enumerate(self.ptrs):
+            d.buffers[r] = p
+        return d
+
+    def close(self):
+        barrier()
+        for p in self._opened:
+            self._L.b200_comm_close(self._C.c_void_p(p))
+        self._opened = []
+        if self.own:
+            self.grads = None
+            self._L.b200_comm_free(self._C.c_void_p(self.own))
+            self.own = None
+
+
 def combine_action_sums(sums, psums, counts, group=None):
     """valid_bilinear.py:61-70 across ranks: per-action fp64 sums and int64 counts add up."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:

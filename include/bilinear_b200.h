@@ -133,6 +133,31 @@ int b200_train_step_host(b200_plan* plan, const float* x_host, const float* y_ho
  * x_host [B][32] -> p_host [B][48].  Asynchronous like b200_train_step_host. */
 int b200_forward_eval_host(b200_plan* plan, const float* x_host, float* p_host, void* stream);
 
+/* ---- data parallel (new; the reference is single-process) -----------------
+ * One process per GPU.  The ONE exchange step of an iteration -- the all-reduce of the flat gradient --
+ * runs INSIDE the persistent kernel over NVLink / NVSwitch peer memory: every rank allocates its gradient
+ * buffer with b200_comm_alloc (cudaMalloc + CUDA IPC handle), the 64-byte handles are exchanged by the host
+ * (torch.distributed all_gather), peers are mapped with b200_comm_open, and b200_plan_set_comm hands the
+ * table to a training plan whose `grads` IS this rank's buffer.  b200_train_step_dp then runs forward,
+ * backward, reduce-scatter + all-gather over peer memory, clip_grad_norm_ and Adam (gradients x
+ * aargs->grad_scale = 1/world) as one kernel; all ranks must call it for the same iteration.
+ * BatchNorm uses each rank's own batch statistics (what DistributedDataParallel does). */
+typedef struct b200_comm_desc {
+  int32_t rank, world;      /* world <= 8 */
+  uint32_t epoch;           /* 0, or the barrier epoch to resume from (shared by all plans of the process) */
+  uint32_t reserved;
+  void* buffers[8];         /* every rank's communication buffer (b200_comm_bytes() each), index = rank */
+} b200_comm_desc;
+int64_t b200_comm_bytes(void);   /* 4 * B200_PARAM_NUMEL + control block */
+int b200_comm_alloc(int64_t bytes, void** dev_ptr, void* handle64);
+int b200_comm_open(const void* handle64, void** peer_ptr);
+int b200_comm_close(void* peer_ptr);
+int b200_comm_free(void* dev_ptr);
+int b200_plan_set_comm(b200_plan* plan, const b200_comm_desc* comm);
+/* epoch_io (host, may be NULL): in = barrier epoch to use (0: the plan's own count), out = next epoch */
+int b200_train_step_dp(b200_plan* plan, const b200_train_args* targs, const b200_adam_args* aargs, uint32_t* epoch_io,
+                       void* stream);
+
 /* clip_grad_norm_ + Adam.step on whatever is in `grads` (train_bilinear.py:81-83). */
 int b200_adam_step(b200_plan* plan, const b200_adam_args* aargs, float* gnorm_out, void* stream);
 

@@ -39,9 +39,14 @@ def main():
     lr = bo.lr_schedule(1)
     for g in opt.param_groups:
         g["lr"] = lr
-    loss, _ = net.train_step(opt, x[lo:hi].to(dev), y[lo:hi].to(dev), max_norm=1.0, update=False)
-    parallel.allreduce_gradients(get_engine(net).flat_g)
-    gnorm = opt.finish_step(max_norm=1.0, grad_scale=1.0 / world)
+    fused = len(sys.argv) > 1 and sys.argv[1] == "fused"
+    if fused:       # in-kernel all-reduce over NVLink peer memory
+        net.enable_data_parallel()
+        loss, gnorm = net.train_step_dp(opt, x[lo:hi].to(dev), y[lo:hi].to(dev), max_norm=1.0)
+    else:           # NCCL all-reduce between two kernels
+        loss, _ = net.train_step(opt, x[lo:hi].to(dev), y[lo:hi].to(dev), max_norm=1.0, update=False)
+        parallel.allreduce_gradients(get_engine(net).flat_g)
+        gnorm = opt.finish_step(max_norm=1.0, grad_scale=1.0 / world)
     torch.cuda.synchronize()
 
     # oracle: every shard separately (local BatchNorm), gradients averaged
@@ -79,7 +84,7 @@ def main():
     ref = flat.clone()
     dist.broadcast(ref, 0)
     same = bool(torch.equal(flat, ref))
-    print("rank %d: loss %.6f (oracle %.6f) |g| %.6f (oracle %.6f) worst rel update err %.2e identical-params %s -> %s"
+    print(("[fused] " if fused else "[nccl] ") + "rank %d: loss %.6f (oracle %.6f) |g| %.6f (oracle %.6f) worst rel update err %.2e identical-params %s -> %s"
           % (rank, float(loss), my_loss, float(gnorm), float(norm_ref), worst, same, "OK" if (ok and same) else "FAIL"),
           flush=True)
     dist.barrier()

@@ -382,6 +382,36 @@ def test_host_buffer_step_equals_device_step(cuda_lib, precision, batch):
         net.train_step_host(opt, x.cuda(), y.cuda())
 
 
+@pytest.mark.parametrize("precision,batch", [("fp32", 64), ("bf16", 4096)])
+def test_in_kernel_allreduce_world_of_one(cuda_lib, precision, batch):
+    """The fused data-parallel step (cross-GPU barriers + reduce-scatter / all-gather through peer-mapped
+    buffers inside the persistent kernel) with a world of ONE rank must reproduce the plain fused step."""
+    x, y, masks = bo.synthetic_batch(29, batch)
+    outs = []
+    for dp in (False, True):
+        net, opt = make_net(4, precision)
+        net.train()
+        if dp:
+            net.enable_data_parallel()
+        net.inject_dropout_masks(masks_tensor(masks))
+        for _ in range(2):      # two iterations: the barrier epochs advance and the buffers are reused
+            if dp:
+                loss, gnorm = net.train_step_dp(opt, x.cuda(), y.cuda(), max_norm=1.0)
+            else:
+                loss, gnorm = net.train_step(opt, x.cuda(), y.cuda(), max_norm=1.0)
+        torch.cuda.synchronize()
+        outs.append((float(loss), float(gnorm), [p.detach().clone() for p in net.parameters()]))
+        if dp:
+            from bilinear_b200.engine import get_engine
+            comm = get_engine(net).comm
+            del net, opt
+            comm.close()
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-5 * abs(outs[0][0])
+    assert abs(outs[0][1] - outs[1][1]) <= 1e-5 * abs(outs[0][1])
+    for a, b in zip(outs[0][2], outs[1][2]):
+        assert float((a - b).abs().max()) <= 2e-6
+
+
 def test_eval_host_buffers(cuda_lib):
     net, _ = make_net(3, "fp32")
     net.eval()
