@@ -344,7 +344,23 @@ def cpu_train_sample(batch, seconds_budget, min_steps=3):
     return batch * n / dt, n, threads, dt
 
 
-def run_reference(args):
+METRIC = "train poses/sec, bilinear MLP (full train_bilinear.py iteration: fwd+MSE+bwd+clip+Adam)"
+
+
+def workload_config(workload, batch, world, fused_dp=True):
+    """`config` of the JSON line -- shared by the B200 arm and the reference (CPU) arm."""
+    if world > 1:
+        par = ("dp%d (local BatchNorm, gradient all-reduce inside the persistent kernel over NVLink peer memory)"
+               if fused_dp else "dp%d (local BatchNorm, NCCL all-reduce of the flat gradient)") % world
+    else:
+        par = "single GPU"
+    return {"workload": "%s: batch %d per GPU, 16 joints, 1024 hidden, 2 residual blocks, random init, "
+                        "Philox dropout, clip_grad_norm 1, Adam" % (workload, batch),
+            "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": par,
+            "l2": "flushed (256 MB fill) between timed iterations" if batch <= 4096 else "activations exceed L2"}
+
+
+def run_reference(args, emit):
     """--impl reference: the CPU arm alone, same metric / config / unit as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -374,22 +390,35 @@ def run_reference(args):
         bo.train_step(st, x, y, masks, lr_for(1))
     dt = time.perf_counter() - t0
     value = batch_sample * steps / dt
+    cfg = workload_config(args.workload, batch, max(args.gpus, 1))
+    cfg["reference_arm"] = ("oracle/bilinear_oracle.py (CPU restatement of the reference's PyTorch path; the reference "
+                            "itself is a Python package and does not travel to the GPU box), batch %d per step on %d "
+                            "host threads, rank 0 only" % (batch_sample, threads))
     line = {
-        "impl": "reference", "metric": "train poses/sec, bilinear MLP (full train_bilinear.py iteration)",
+        "impl": "reference", "metric": METRIC,
         "value": value, "unit": "poses/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "batch_per_step": batch_sample, "device": "cpu"},
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "poses/s", "cores": threads, "kind": "port",
                          "sample": "%d iterations of batch %d (oracle/bilinear_oracle.py, float32, torch CPU ops)"
                                    % (steps, batch_sample)},
         "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ main
 def main():
+    # the contract is ONE JSON line on stdout: anything libraries write to file descriptor 1 (e.g. NCCL's
+    # version banner) is sent to stderr instead, and the line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -400,7 +429,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
 
     import torch
@@ -456,25 +485,17 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": "train poses/sec, bilinear MLP (full train_bilinear.py iteration: fwd+MSE+bwd+clip+Adam)",
+            "metric": METRIC,
             "value": main_res["value"], "unit": "poses/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-            "config": {"workload": "%s: batch %d per GPU, 16 joints, 1024 hidden, 2 residual blocks, random init, "
-                                   "Philox dropout, clip_grad_norm 1, Adam" % (args.workload, batch),
-                       "batch_per_gpu": batch, "global_batch": batch * world,
-                       "parallelism": ("dp%d (local BatchNorm, gradient all-reduce inside the persistent kernel over "
-                                       "NVLink peer memory)" if os.environ.get("BILINEAR_B200_DP", "fused") == "fused" else
-                                       "dp%d (local BatchNorm, NCCL all-reduce of the flat gradient)") % world
-                       if world > 1 else "single GPU",
-                       "l2": "flushed (256 MB fill) between timed iterations" if batch <= 4096 else
-                             "activations exceed L2"},
+            "config": workload_config(args.workload, batch, world, os.environ.get("BILINEAR_B200_DP", "fused") == "fused"),
             "roofline": main_res["roofline"], "e2e": main_res.get("e2e"),
             "gpu_launches": main_res["launches"], "clocks": clocks, "cpu_baseline": cpu,
             "ms_per_step_warm_l2": main_res.get("ms_per_step_warm_l2"),
             "also": also,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -303,7 +303,10 @@ static int end_phase(b200_plan* pl) {
       for (int t = 0; t < g.num_tiles; ++t, ++id) {
         const int ks = t / (g.m_tiles * g.n_tiles);
         const int kb = std::min(num_kb, (ks + 1) * g.kb_per_split) - ks * g.kb_per_split;
-        tiles.push_back(T{id, int64_t(kb) * pairs * g.BN + 6 * g.BN});
+        // k-blocks x width, plus an epilogue term; the large-batch dgrad epilogue (z / keep / residual loads,
+        // g or dy store, statistics) measures about as long as its 16 k-block mainloop
+        const int64_t epi = (g.epi == EPI_DGRAD_LARGE) ? 16 * g.BN : 6 * g.BN;
+        tiles.push_back(T{id, int64_t(kb) * pairs * g.BN + epi});
       }
     }
     std::stable_sort(tiles.begin(), tiles.end(), [](const T& a, const T& b) { return a.cost > b.cost; });
@@ -515,8 +518,10 @@ static int build_decode(b200_plan* pl, bool fuse_loss, bool train) {
   return 0;
 }
 
-// K slices of a large-batch wgrad GEMM (K = batch): slices of about 32 k-blocks weigh as much as two
-// dgrad tiles, so the longest-first schedule balances the phase to within one such slice.
+// K slices of a large-batch wgrad GEMM (K = batch): slices of 32 k-blocks weigh as much as two dgrad
+// mainloops, so the longest-first schedule balances the phase to within one such slice.  (Measured: 128
+// k-block slices cut the L2 reduction traffic 4x but leave ~100 us of imbalance per phase, because the
+// dgrad tiles are epilogue-bound and cost more than their k-blocks suggest -- see profiles/.)
 static int wgrad_split(const b200_plan* pl) {
   if (!pl->large) return 1;
   const int num_kb = (pl->B + 63) / 64;

@@ -87,9 +87,32 @@ def main():
     print(("[fused] " if fused else "[nccl] ") + "rank %d: loss %.6f (oracle %.6f) |g| %.6f (oracle %.6f) worst rel update err %.2e identical-params %s -> %s"
           % (rank, float(loss), my_loss, float(gnorm), float(norm_ref), worst, same, "OK" if (ok and same) else "FAIL"),
           flush=True)
+    # many iterations back to back (Philox dropout, no host synchronisation in between)
+    net.inject_dropout_masks(None)
+    xs, ys = x[lo:hi].to(dev), y[lo:hi].to(dev)
+    n_more = 200
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(n_more):
+        if fused:
+            net.train_step_dp(opt, xs, ys, max_norm=1.0)
+        else:
+            net.train_step(opt, xs, ys, max_norm=1.0, update=False)
+            parallel.allreduce_gradients(get_engine(net).flat_g)
+            opt.finish_step(max_norm=1.0, grad_scale=1.0 / world)
+    ev1.record()
+    torch.cuda.synchronize()
+    flat = get_engine(net).flat_p.clone()
+    ref = flat.clone()
+    dist.broadcast(ref, 0)
+    same2 = bool(torch.equal(flat, ref))
+    print("rank %d: %d more iterations, %.1f us each, parameters identical across ranks: %s"
+          % (rank, n_more, ev0.elapsed_time(ev1) * 1e3 / n_more, same2), flush=True)
     dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if (ok and same) else 1)
+    sys.exit(0 if (ok and same and same2) else 1)
 
 
 if __name__ == "__main__":
