@@ -37,6 +37,22 @@ SPACER_CYCLES = 600_000                     # ~0.3 ms at 1.9 GHz
 EVAL_BYTES_PER_POSE = 384                   # 2 x 16 x 3 x 4 read (+ 4 written when per-pose output is kept)
 
 
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` summary under profiles/ (bytes), or None."""
+    path = os.path.join(ROOT, "profiles", name)
+    try:
+        tot = 0.0
+        with open(path) as f:
+            for line in f:
+                k, unit, v = line.rstrip("\n").split(",")[:3]
+                if k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(v) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        return tot or None
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -245,12 +261,15 @@ def bench_train(args, precision, batch, steps, warmup, device, world, peaks, flu
     if batch <= 256:
         ach = ADAM_BYTES_PER_STEP / (ms_step * 1e-3) / 1e9
         res["roofline"] = dict(bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"],
-                               traffic=None, peak_source=peaks["source"],
+                               traffic=ncu_traffic("r1h_train_step_b64_fp32_ncu_full.csv") if precision == "fp32" else None,
+                               traffic_source="profiles/r1h_train_step_b64_fp32_ncu_full.csv (bytes per launch)",
+                               peak_source=peaks["source"],
                                algorithmic="6 x 4 B x 4 291 632 parameters (Adam p,m,v read+write) per step")
     else:
         ach = FLOP_PER_POSE_TRAIN * batch / (ms_step * 1e-3) / 1e12
         pk = peaks["bf16_sustained"]
-        res["roofline"] = dict(bound="tensor", achieved=ach, peak=pk, unit="TFLOP/s", frac=ach / pk, traffic=None,
+        res["roofline"] = dict(bound="tensor", achieved=ach, peak=pk, unit="TFLOP/s", frac=ach / pk,
+                               traffic=ncu_traffic("r1g_train_step_b65536_bf16_ncu_full.csv") if batch == 65536 else None,
                                peak_source=peaks["source"] + " (sustained bf16 cuBLAS)",
                                algorithmic="25 591 808 FLOP/pose x %d poses per step" % batch)
     return res
