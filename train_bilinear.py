@@ -74,6 +74,9 @@ def main(cfg=None, save_root='save'):
         writer = SummaryWriter(log_dir='{log_dir}/visualize'.format(log_dir=log_dir))
 
     bilinear.train()
+    if world > 1:
+        # one process per GPU: peer-mapped gradient buffers for the in-kernel all-reduce
+        bilinear.enable_data_parallel()
     gen = torch.Generator().manual_seed(int(torch.initial_seed()) & 0x7fffffff)   # same permutation on every rank
     global_batch = cfg.batch_size * world
     steps_per_epoch = (len(data) + global_batch - 1) // global_batch
@@ -99,11 +102,8 @@ def main(cfg=None, save_root='save'):
             # zero_grad, forward, MSELoss, backward, clip_grad_norm_(max_norm=1), optimizer.step
             if world == 1:
                 loss, _ = bilinear.train_step(optimizer, part, S, max_norm=1)
-            else:
-                from bilinear_b200.engine import get_engine
-                loss, _ = bilinear.train_step(optimizer, part, S, max_norm=1, update=False)
-                parallel.allreduce_gradients(get_engine(bilinear).flat_g)
-                optimizer.finish_step(max_norm=1, grad_scale=1.0 / world)
+            else:   # gradients averaged over the ranks inside the same kernel (NVLink peer memory)
+                loss, _ = bilinear.train_step_dp(optimizer, part, S, max_norm=1)
             ring[k].copy_(loss)
             k += 1
             if progress:
