@@ -532,7 +532,7 @@ static int wgrad_split(const b200_plan* pl) {
 // BN/ReLU/dropout backward of layer l behind it, wgrad(l+1) } then wgrad(0).  The dgrad GEMMs read the
 // [out][in] weight planes as an MN-major A operand (no transposed copy of the weights exists).
 // `tail_ew`: elementwise job appended to the last (wgrad 0) phase, or nullptr.
-static int build_backward(b200_plan* pl, bool with_norm, const Args* tail_ew, int tail_kind) {
+static int build_backward(b200_plan* pl, bool with_norm, const Args* tail_ew, int tail_kind, bool prefetch_opt = false) {
   const Bufs& u = pl->u;
   const b200_plan_desc& d = pl->d;
   const int B = pl->B;
@@ -555,6 +555,10 @@ static int build_backward(b200_plan* pl, bool with_norm, const Args* tail_ew, in
     const int Kd = kPL.rows[up];               // 1024, or 48 for decode
     const PlaneRef& dzu = (up == 5) ? u.dP_fm : u.dz_fm[up];
     begin_phase(pl);
+    if (!pl->large && prefetch_opt) {
+      pl->cur.ph.pf_slice = 4 - l;
+      pl->cur.ph.pf_slices = 5;
+    }
     if (!pl->large) {
       small_part_args(pl, a);
       if (add_gemm(pl, u.W[up], 1, dzu, 1, kHidden, B, Kd, tile_bn(pl, B), EPI_PARTIAL, a, kSmallSplit)) return 1;
@@ -696,7 +700,7 @@ static int build_plan(b200_plan* pl) {
     if (build_fwd_layer(pl, l, true, l == 0 && !pl->large)) return 1;
   if (build_decode(pl, true, true)) return 1;
   if (!pl->large) {
-    if (build_backward(pl, true, nullptr, 0)) return 1;
+    if (build_backward(pl, true, nullptr, 0, true)) return 1;
   } else {
     Args a = adam_args(pl);
     if (wgrad_split(pl) == 1) {
@@ -750,7 +754,7 @@ static int build_plan(b200_plan* pl) {
   for (int l = 0; l < kNumHeavy; ++l)
     if (build_fwd_layer(pl, l, true, l == 0 && !pl->large)) return 1;
   if (build_decode(pl, true, true)) return 1;
-  if (build_backward(pl, false, nullptr, 0)) return 1;      // the clipping norm is taken on the REDUCED gradient
+  if (build_backward(pl, false, nullptr, 0, true)) return 1;   // the clipping norm is taken on the REDUCED gradient
   for (int k = 0; k < 3; ++k) {
     Args a = base_args(pl, 0);
     a.comm = u.comm_tab;
@@ -778,6 +782,7 @@ static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, c
   p.cta_tiles = pl->u.cta_tiles + size_t(s.first) * pl->sms;
   p.tmaps = pl->u.tmaps;
   p.sched = pl->u.sched;
+  p.adam = (pl->d.exp_avg && pl->d.exp_avg_sq) ? pl->u.adam_tab : nullptr;
   p.barrier = pl->u.barrier;
   p.phase_ns = pl->u.phase_ns;
   pl->last_first = s.first; pl->last_count = count;

@@ -217,7 +217,8 @@ struct Phase {
   int32_t num_stages;
   int32_t sched_off;              // < 0: tiles are strided over CTAs; else offset into MegaParams::sched of the
                                   // tile-id lists (CtaTiles::begin/end index into it)
-  int32_t pad[2];
+  int32_t pf_slice, pf_slices;    // pf_slices > 0: during this phase an idle warp prefetches slice pf_slice of
+                                  // pf_slices of the optimizer's p / m / v arrays into L2 (MegaParams::adam)
 };
 
 // Everything a CTA needs to know about one phase, contiguous in device memory.  All 256 threads copy
@@ -244,6 +245,7 @@ struct MegaParams {
   const CtaTiles* cta_tiles;  // [num_phases][gridDim.x] (nullptr: every phase is strided)
   const void* tmaps;        // array of CUtensorMap (128 B each, 64 B aligned)
   const int32_t* sched;     // per-phase tile lists (see Phase::sched_off)
+  const AdamTab* adam;      // optimizer arrays for the L2 prefetch (Phase::pf_slices), or nullptr
   unsigned int* barrier;    // grid barrier counter: monotonic across launches (never reset), see bar_base
   unsigned long long* phase_ns;  // [8 * (num_phases + 1)] globaltimer stamps written by block 0 (nullptr: off)
   int32_t num_phases;
