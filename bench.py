@@ -148,8 +148,14 @@ class TrainLoop:
         g = torch.Generator(device="cpu").manual_seed(1234 + parallel.env_world()[0])
         self.xs = [torch.randn(batch, 32, generator=g).to(device) for _ in range(nbatches)]
         self.ys = [torch.randn(batch, 48, generator=g).to(device) for _ in range(nbatches)]
-        self.hx = [x.cpu().pin_memory() for x in self.xs[:8]]
-        self.hy = [y.cpu().pin_memory() for y in self.ys[:8]]
+        # pinned host batches as a DataLoader(pin_memory=True) delivers them; x and y of one batch share a
+        # pinned block [x | y] so that the library can move them with a single copy
+        self.hx, self.hy = [], []
+        for x, y in zip(self.xs[:8], self.ys[:8]):
+            blk = torch.empty(batch * 80, dtype=torch.float32).pin_memory()
+            hx, hy = blk[:batch * 32].view(batch, 32), blk[batch * 32:].view(batch, 48)
+            hx.copy_(x.cpu()); hy.copy_(y.cpu())
+            self.hx.append(hx); self.hy.append(hy)
         self.i = 0
 
     def _lr(self):

@@ -181,8 +181,8 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
   u.comm_tab = c.take_n<CommTab>(1);
   u.part = large ? nullptr : c.take_n<float>(int64_t(kSmallSplit) * kHidden * Bs);
   u.x_save = large ? nullptr : c.take_n<float>(Bs * kDin);
-  u.x_stage = c.take_n<float>(Bs * kDin);
-  u.y_stage = c.take_n<float>(Bs * kDout);
+  u.x_stage = c.take_n<float>(Bs * (kDin + kDout));   // [x | y]: y starts right after the B x 32 block of x
+  u.y_stage = u.x_stage ? u.x_stage + int64_t(B) * kDin : nullptr;
   u.p_stage = c.take_n<float>(Bs * kDout);
   u.scalars = c.take_n<float>(16);
   // accumulators cleared at the start of every step (one contiguous region)
@@ -997,14 +997,35 @@ int b200_train_step_host(b200_plan* plan, const float* x_host, const float* y_ho
   if (!plan || !x_host || !y_host || !targs || !out_host) return fail("null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t B = size_t(plan->B);
-  CK(cudaMemcpyAsync(plan->u.x_stage, x_host, B * kDin * sizeof(float), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(plan->u.y_stage, y_host, B * kDout * sizeof(float), cudaMemcpyHostToDevice, st));
+  // x and y live next to each other in the workspace: when the caller's batches are adjacent in host
+  // memory too (one pinned [x | y] block) they travel as ONE copy
+  bool one_copy = false;
+  if (y_host == x_host + B * kDin) {
+    // adjacent addresses may still be two separate pinned allocations: then the copy is rejected up front
+    // (synchronously, nothing enqueued) and the batches go one by one
+    one_copy = cudaMemcpyAsync(plan->u.x_stage, x_host, B * (kDin + kDout) * sizeof(float), cudaMemcpyHostToDevice, st) ==
+               cudaSuccess;
+    if (!one_copy) cudaGetLastError();
+  }
+  if (!one_copy) {
+    CK(cudaMemcpyAsync(plan->u.x_stage, x_host, B * kDin * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(plan->u.y_stage, y_host, B * kDout * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
   b200_train_args t = *targs;
   t.x = plan->u.x_stage; t.y = plan->u.y_stage;
-  t.loss_out = plan->u.scalars; t.gnorm_out = plan->u.scalars + 1;
+  // the two result scalars are stored straight into the caller's host memory when the device can address
+  // it (pinned memory under unified addressing): no device -> host copy operation at all
+  float* dev_view = nullptr;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, out_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+    dev_view = reinterpret_cast<float*>(attr.devicePointer);
+  else
+    cudaGetLastError();   // pageable memory: not an error, fall back to a copy
+  t.loss_out = dev_view ? dev_view : plan->u.scalars;
+  t.gnorm_out = dev_view ? dev_view + 1 : plan->u.scalars + 1;
   int rc = b200_train_step(plan, &t, aargs, update, stream);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(out_host, plan->u.scalars, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (!dev_view) CK(cudaMemcpyAsync(out_host, plan->u.scalars, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
   return 0;
 }
 

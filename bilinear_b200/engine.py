@@ -327,34 +327,34 @@ class Engine:
 
     def train_step_host(self, x_host, y_host, adam, update=True):
         """train_bilinear.py:62-88 with its transfers: x_host [B, 32] / y_host [B, 48] are CPU tensors
-        (pinned for asynchronous copies); copies in, the one-kernel step, and the copy of (loss, grad norm)
+        (pinned for asynchronous copies); copies in, the one-kernel step, and the (loss, grad norm) written
         back to pinned host memory are enqueued by ONE library call; returns the two Python floats after
         synchronising the stream (the reference reads loss.item() every step as well)."""
         if x_host.is_cuda or y_host.is_cuda:
             raise RuntimeError("train_step_host() takes CPU tensors; use train_step() for CUDA tensors")
-        if x_host.dim() != 2 or x_host.shape[1] != 32 or y_host.shape != (x_host.shape[0], 48):
+        B = x_host.shape[0]
+        if x_host.dim() != 2 or x_host.shape[1] != 32 or y_host.dim() != 2 or y_host.shape[0] != B or y_host.shape[1] != 48:
             raise RuntimeError("expected x [B, 32] and y [B, 48]")
         if x_host.dtype != torch.float32 or y_host.dtype != torch.float32 or not x_host.is_contiguous() \
                 or not y_host.is_contiguous():
             x_host, y_host = x_host.float().contiguous(), y_host.float().contiguous()
-        B = x_host.shape[0]
         if B < 2:
             raise ValueError("Expected more than 1 value per channel when training, got input size %s"
                              % str(torch.Size([B, 1024])))
         pl = self.plan(B, PLAN_TRAIN)
         if self.host_out is None:
             self.host_out = torch.zeros(2, dtype=torch.float32).pin_memory()
+            self.host_out_np = self.host_out.numpy()
         t = self._train_args(None, None, None, B)
         stream = torch.cuda.current_stream()
-        check(_lib.lib().b200_train_step_host(pl.handle, C.c_void_p(x_host.data_ptr()), C.c_void_p(y_host.data_ptr()),
-                                              C.byref(t), C.byref(adam), 1 if update else 0,
-                                              C.c_void_p(self.host_out.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        check(_lib.lib().b200_train_step_host(pl.handle, x_host.data_ptr(), y_host.data_ptr(), C.byref(t), C.byref(adam),
+                                              1 if update else 0, self.host_out.data_ptr(), stream.cuda_stream))
         self.fwd_counter += 1
         self.pending_backward = None
         if update:
             pl.weights_version = self.weights_version = self.weights_version + 1
         stream.synchronize()
-        return float(self.host_out[0]), float(self.host_out[1])
+        return float(self.host_out_np[0]), float(self.host_out_np[1])
 
     def forward_eval_host(self, x_host, out_host=None):
         """valid_bilinear.py:39-52 with its transfers: CPU x [B, 32] -> CPU prediction [B, 48] (pinned)."""
