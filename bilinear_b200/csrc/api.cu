@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -19,7 +20,7 @@
 #include "jobs.h"
 
 namespace b200 {
-cudaError_t launch_mega(const MegaParams& p, int grid, bool cooperative, cudaStream_t stream);
+cudaError_t launch_mega(const MegaParams& p, int grid, bool cooperative, cudaStream_t stream, int cg);
 int mega_ring_bytes();
 struct EvalParams {
   const float* pred; const float* gt; const float* mean; const float* stddev; const int32_t* action;
@@ -247,6 +248,8 @@ struct b200_plan {
   int B, P, kind;
   bool large;
   int sms;
+  int cg = 1;                // CTAs per MMA: 2 = CTA pairs (large-batch plans), 1 otherwise
+  int workers() const { return sms / cg; }
   std::vector<CUtensorMap> tm;
   std::vector<PhaseBlob> blobs;
   std::vector<CtaTiles> cta_tiles;   // [phase][sms]
@@ -281,11 +284,11 @@ static int end_phase(b200_plan* pl) {
   for (int j = 0; j < p.num_gemm; ++j) {
     const GemmJob& g = pl->cur.gj[j];
     p.gemm_tiles += g.num_tiles;
-    sb = std::max(sb, g.a.planes * (128 * 128 + g.BN * 128));
+    sb = std::max(sb, g.a.planes * (128 * 128 + (g.BN / pl->cg) * 128));
   }
   p.stage_bytes = sb;
   p.num_stages = std::max(1, std::min(8, mega_ring_bytes() / sb));
-  const int G = pl->sms;
+  const int G = pl->workers();   // CTAs, or CTA pairs walking one tile list
   std::vector<CtaTiles> ct(G);
   for (int c = 0; c < G; ++c) memset(&ct[c], 0, sizeof(CtaTiles));
   if (p.gemm_tiles > 0) {
@@ -357,10 +360,13 @@ static int add_gemm(b200_plan* pl, const PlaneRef& A, int a_mn, const PlaneRef& 
   GemmJob g;
   memset(&g, 0, sizeof g);
   if (a_mn ? add_map(pl, A, M, K, 64, &g.tmap_a) : add_map(pl, A, K, M, 128, &g.tmap_a)) return 1;
-  if (b_mn ? add_map(pl, Bop, N, K, 64, &g.tmap_b) : add_map(pl, Bop, K, N, BN, &g.tmap_b)) return 1;
+  const int cg = pl->cg;
+  if (cg == 2 && (BN % 32 || (b_mn && BN % 128))) return fail("CTA-pair tile width must split into two halves");
+  // CTA pairs: a tile is 256 rows of A (128 per CTA) and each CTA loads half of the B tile
+  if (b_mn ? add_map(pl, Bop, N, K, 64, &g.tmap_b) : add_map(pl, Bop, K, N, BN / cg, &g.tmap_b)) return 1;
   g.a_mn = a_mn; g.b_mn = b_mn;
   g.M = M; g.N = N; g.K = K; g.BN = BN;
-  g.m_tiles = (M + 127) / 128;
+  g.m_tiles = (M + 128 * cg - 1) / (128 * cg);
   g.n_tiles = (N + BN - 1) / BN;
   const int num_kb = (K + 63) / 64;
   ksplit = std::max(1, std::min(ksplit, num_kb));
@@ -779,7 +785,7 @@ static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, c
   MegaParams p;
   memset(&p, 0, sizeof p);
   p.blobs = pl->u.blobs + s.first;
-  p.cta_tiles = pl->u.cta_tiles + size_t(s.first) * pl->sms;
+  p.cta_tiles = pl->u.cta_tiles + size_t(s.first) * pl->workers();
   p.tmaps = pl->u.tmaps;
   p.sched = pl->u.sched;
   p.adam = (pl->d.exp_avg && pl->d.exp_avg_sq) ? pl->u.adam_tab : nullptr;
@@ -790,8 +796,9 @@ static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, c
   p.dyn = dyn;
   const bool coop = count > 1;
   p.bar_base = pl->bar_count;
-  pl->bar_count += uint32_t(pl->sms) * uint32_t(count - 1);
-  CK(launch_mega(p, pl->sms, coop, stream));
+  const int grid = pl->workers() * pl->cg;
+  pl->bar_count += uint32_t(grid) * uint32_t(count - 1);
+  CK(launch_mega(p, grid, coop, stream, pl->cg));
   g_launches.fetch_add(1);
   return 0;
 }
@@ -853,6 +860,9 @@ int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
   pl->d = *desc;
   pl->B = desc->batch; pl->P = desc->precision; pl->kind = desc->kind;
   pl->large = pl->B > (pl->P == 1 ? 256 : 128);
+  // large batches: CTA pairs (tcgen05 cta_group::2) -- a third less operand traffic per MMA block through the
+  // L2 -> SM path that bounds these GEMMs.  B200_CG=1 keeps single-CTA MMAs (A/B comparison).
+  pl->cg = (pl->large && !(getenv("B200_CG") && atoi(getenv("B200_CG")) == 1)) ? 2 : 1;
   int dev = 0;
   cudaGetDevice(&dev);
   pl->sms = 148;
@@ -1181,7 +1191,7 @@ int b200_debug_gemm(const uint16_t* a, const uint16_t* b, float* dmat, int32_t m
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  CK(launch_mega(p, std::min(sms, g.num_tiles), false, st));
+  CK(launch_mega(p, std::min(sms, g.num_tiles), false, st, 1));
   g_launches.fetch_add(1);
   return 0;
 }
