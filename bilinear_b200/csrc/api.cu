@@ -860,9 +860,11 @@ int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
   pl->d = *desc;
   pl->B = desc->batch; pl->P = desc->precision; pl->kind = desc->kind;
   pl->large = pl->B > (pl->P == 1 ? 256 : 128);
-  // large batches: CTA pairs (tcgen05 cta_group::2) -- a third less operand traffic per MMA block through the
-  // L2 -> SM path that bounds these GEMMs.  B200_CG=1 keeps single-CTA MMAs (A/B comparison).
-  pl->cg = (pl->large && !(getenv("B200_CG") && atoi(getenv("B200_CG")) == 1)) ? 2 : 1;
+  // B200_CG=2 runs large-batch plans on CTA pairs (tcgen05 cta_group::2: M = 256 per MMA, each CTA loads half
+  // of the B tile).  Measured at B = 65536 it is no faster on the K = 1024 phases -- they are bound by the
+  // epilogue and TMA issue rate, not by operand bytes -- and slower on the 48-row decode layer, so single-CTA
+  // MMAs stay the default.
+  pl->cg = (pl->large && getenv("B200_CG") && atoi(getenv("B200_CG")) == 2) ? 2 : 1;
   int dev = 0;
   cudaGetDevice(&dev);
   pl->sms = 148;
