@@ -519,7 +519,16 @@ static int build_decode(b200_plan* pl, bool fuse_loss, bool train) {
     return 0;
   }
   begin_phase(pl);
-  if (add_gemm(pl, u.W[5], 0, u.h_fm[4], 1, kDout, pl->B, kHidden, tile_bn(pl, pl->B), EPI_DECODE, a)) return 1;
+  if (pl->cg == 1) {
+    // Large batches: the decode GEMM runs TRANSPOSED -- P[b][48] = h[b][:] . W5^T with the activations as an
+    // MN-major A operand (128 poses per tile) and the 48 x 1024 weight as the K-major B operand.  With rows =
+    // output features only 48 of the 128 accumulator lanes (1.5 of the 4 epilogue warps) carry data and every
+    // prediction / target access is a 4-byte access at a 192-byte stride; with rows = poses each lane owns
+    // one pose: 192 contiguous bytes of target in, 192 contiguous bytes of prediction out.
+    if (add_gemm(pl, u.h_fm[4], 1, u.W[5], 0, pl->B, kDout, kHidden, kDout, EPI_DECODE_T, a)) return 1;
+  } else {
+    if (add_gemm(pl, u.W[5], 0, u.h_fm[4], 1, kDout, pl->B, kHidden, tile_bn(pl, pl->B), EPI_DECODE, a)) return 1;
+  }
   if (end_phase(pl)) return 1;
   return 0;
 }

@@ -36,6 +36,7 @@ enum EpiKind : int32_t {
   EPI_FWD_LARGE = 2,   // bias, write z, per-tile partial sum / sumsq -> stats
   EPI_FWD_EVAL = 3,    // scale*acc+shift, ReLU (+skip)            (BN folded, eval mode)
   EPI_DECODE = 4,      // bias -> p[b][48]; optional fused MSE loss + dP
+  EPI_DECODE_T = 5,    // the same with the GEMM transposed: rows = poses, 48 columns (large-batch plans)
   EPI_DGRAD_LARGE = 6, // da (+skip grad) -> dy, partial sum(dy), sum(dy*xhat) -> stats
   EPI_WGRAD = 7,       // dW tile -> flat grad buffer + sum of squares (ksplit > 1: vector reductions)
 };

@@ -10,7 +10,7 @@ from bilinear_b200.engine import get_engine
 from bilinear_b200._lib import PLAN_INFER, PLAN_TRAIN
 from bilinear_b200.model import bilinear as mb
 
-EPI = ["STORE", "PARTIAL", "FWD_LARGE", "FWD_EVAL", "DECODE", "-", "DGRAD_LARGE", "WGRAD"]
+EPI = ["STORE", "PARTIAL", "FWD_LARGE", "FWD_EVAL", "DECODE", "DECODE_T", "DGRAD_LARGE", "WGRAD"]
 EW = ["PREP", "DROPBITS", "BN_FOLD", "BN_FWD_APPLY", "BN_BWD_APPLY", "SPLIT_DP", "SUMSQ", "ADAM", "SPLIT_W",
       "BN_FWD_SMALL", "BN_BWD_SMALL", "DECODE_SMALL"]
 
