@@ -353,6 +353,14 @@ def test_fused_train_step(cuda_lib, precision, batch):
     assert float(opt.state_dict()["state"][0]["step"]) == 4.0
 
 
+@pytest.mark.parametrize("precision,batch", [("bf16", 1000), ("fp32", 300), ("bf16", 4096)])
+def test_fused_train_step_cta_pairs(cuda_lib, monkeypatch, precision, batch):
+    """The same iteration through the cta_group::2 build of the kernel (csrc/mega_pair.cu: clusters of two CTAs
+    share every MMA, M = 256; opt-in with B200_CG=2, read when the plan is created)."""
+    monkeypatch.setenv("B200_CG", "2")
+    test_fused_train_step(cuda_lib, precision, batch)
+
+
 @pytest.mark.parametrize("precision,batch", [("fp32", 64), ("bf16", 1000)])
 def test_host_buffer_step_equals_device_step(cuda_lib, precision, batch):
     """b200_train_step_host (pinned host batches in, loss / gradient norm out) is the same iteration as
