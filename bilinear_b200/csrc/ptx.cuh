@@ -87,6 +87,22 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// The same load with raw shared-window addresses (destination, mbarrier): CG = 2 is the CTA-pair form whose
+// transaction bytes are counted on the leader CTA's barrier (pass the barrier address with the peer bit cleared).
+template <int CG>
+__device__ __forceinline__ void tma_load_3d_raw(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // CTA-pair variant: executed by both CTAs; the transaction bytes are counted on the barrier of the LEADER CTA
 // (cluster rank 0) -- the peer bit of the shared::cluster barrier address is cleared.
 __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
