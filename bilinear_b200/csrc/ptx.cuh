@@ -137,6 +137,9 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// One line into L2 (LSU path, not the TMA unit).
+__device__ __forceinline__ void prefetch_l2(const void* gptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr)); }
+
 // Bulk prefetch of `bytes` (multiple of 16) of global memory into L2; no shared memory, no completion.
 __device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
