@@ -267,15 +267,15 @@ def bench_train(args, precision, batch, steps, warmup, device, world, peaks, flu
     if batch <= 256:
         ach = ADAM_BYTES_PER_STEP / (ms_step * 1e-3) / 1e9
         res["roofline"] = dict(bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"],
-                               traffic=ncu_traffic("r1m_train_step_b64_fp32_ncu_full.csv") if precision == "fp32" else None,
-                               traffic_source="profiles/r1m_train_step_b64_fp32_ncu_full.csv (bytes per launch)",
+                               traffic=ncu_traffic("r1p_train_step_b64_fp32_ncu_full.csv") if precision == "fp32" else None,
+                               traffic_source="profiles/r1p_train_step_b64_fp32_ncu_full.csv (bytes per launch)",
                                peak_source=peaks["source"],
                                algorithmic="6 x 4 B x 4 291 632 parameters (Adam p,m,v read+write) per step")
     else:
         ach = FLOP_PER_POSE_TRAIN * batch / (ms_step * 1e-3) / 1e12
         pk = peaks["bf16_sustained"]
         res["roofline"] = dict(bound="tensor", achieved=ach, peak=pk, unit="TFLOP/s", frac=ach / pk,
-                               traffic=ncu_traffic("r1m_train_step_b65536_bf16_ncu_full.csv") if batch == 65536 else None,
+                               traffic=ncu_traffic("r1p_train_step_b65536_bf16_ncu_full.csv") if batch == 65536 else None,
                                peak_source=peaks["source"] + " (sustained bf16 cuBLAS)",
                                algorithmic="25 591 808 FLOP/pose x %d poses per step" % batch)
     return res
