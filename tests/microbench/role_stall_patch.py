@@ -18,9 +18,10 @@ a=rep(a,"  p.dyn = dyn;\n","  p.dyn = dyn;\n  p.dbg = getenv(\"B200_DBG\") ? ato
 a=rep(a,"    for (int k = 1; k < 8; ++k) ns_out[8 * i + k] = t[8 * i + k] >= t[8 * i] ? int64_t(t[8 * i + k] - t[8 * i]) : -1;","    for (int k = 1; k < 8; ++k) ns_out[8 * i + k] = int64_t(t[8 * i + k]);")
 open(d+'api.cu','w').write(a)
 s=open(d+'mega.cu').read()
-s=rep(s,'SmemCtl* ctl, Ring& pipe, int rank, uint32_t elected) {','SmemCtl* ctl, Ring& pipe, int rank, uint32_t elected, long long& stall) {')
-s=rep(s,'    mbar_wait(&ctl->empty[pipe.stage], pipe.parity(), 100);\n','    { long long t0 = clock64(); mbar_wait(&ctl->empty[pipe.stage], pipe.parity(), 100); stall += clock64() - t0; }\n')
-s=rep(s,"    if (elected) {\n      if (CG == 1 || rank == 0) mbar_expect_tx(full, tx);\n","    if (p.dbg & 1) { if (elected && (CG == 1 || rank == 0)) mbar_arrive(full); pipe.advance(phs.num_stages); continue; }\n    if (elected) {\n      if (CG == 1 || rank == 0) mbar_expect_tx(full, tx);\n")
+s=rep(s,"SmemCtl* ctl, Ring& pipe, int rank, uint32_t elected) {\n  // The operand layouts are compile-time here","SmemCtl* ctl, Ring& pipe, int rank, uint32_t elected, long long& stall) {\n  // The operand layouts are compile-time here")
+s=rep(s,"SmemCtl* ctl, Ring& pipe, int rank, uint32_t elected) {\n  const int a_mn = tr.job->a_mn, b_mn = tr.job->b_mn;","SmemCtl* ctl, Ring& pipe, int rank, uint32_t elected, long long& stall) {\n  const int a_mn = tr.job->a_mn, b_mn = tr.job->b_mn;")
+s=rep(s,"(p, phs, tr, smem, ctl, pipe, rank, elected);","(p, phs, tr, smem, ctl, pipe, rank, elected, stall);",0)
+s=rep(s,'    mbar_wait(&ctl->empty[pipe.stage], pipe.parity(), 100);\n    if (elected) {\n      const uint32_t full =','    { long long t0 = clock64(); mbar_wait(&ctl->empty[pipe.stage], pipe.parity(), 100); stall += clock64() - t0; }\n    if (p.dbg & 1) { if (elected && (CG == 1 || rank == 0)) mbar_arrive(&ctl->full[pipe.stage]); pipe.advance(phs.num_stages); continue; }\n    if (elected) {\n      const uint32_t full =')
 s=rep(s,'                                         Pipe& acc, uint32_t tmem_base, uint32_t elected) {','                                         Pipe& acc, uint32_t tmem_base, uint32_t elected, long long& stall_full, long long& stall_acc, long long& t_issue, int dbg) {')
 s=rep(s,'  mbar_wait(&ctl->tmem_empty[acc.stage], acc.phase ^ 1u, 200);\n','  { long long t0 = clock64(); mbar_wait(&ctl->tmem_empty[acc.stage], acc.phase ^ 1u, 200); stall_acc += clock64() - t0; }\n')
 s=rep(s,'      mbar_wait(&ctl->full[pipe.stage], pipe.parity(), 201);\n','      long long t0 = clock64(); mbar_wait(&ctl->full[pipe.stage], pipe.parity(), 201); long long t1 = clock64(); stall_full += t1 - t0;\n', 0)
