@@ -361,7 +361,7 @@ static int add_gemm(b200_plan* pl, const PlaneRef& A, int a_mn, const PlaneRef& 
   memset(&g, 0, sizeof g);
   if (a_mn ? add_map(pl, A, M, K, 64, &g.tmap_a) : add_map(pl, A, K, M, 128, &g.tmap_a)) return 1;
   const int cg = pl->cg;
-  if (cg == 2 && (BN % 32 || (b_mn && BN % 128))) return fail("CTA-pair tile width must split into two halves");
+  if (cg == 2 && ((BN / 2) % 8 || BN % 16 || (b_mn && BN % 128))) return fail("CTA-pair tile width must split into two halves");
   // CTA pairs: a tile is 256 rows of A (128 per CTA) and each CTA loads half of the B tile
   if (b_mn ? add_map(pl, Bop, N, K, 64, &g.tmap_b) : add_map(pl, Bop, K, N, BN / cg, &g.tmap_b)) return 1;
   g.a_mn = a_mn; g.b_mn = b_mn;
@@ -519,15 +519,13 @@ static int build_decode(b200_plan* pl, bool fuse_loss, bool train) {
     return 0;
   }
   begin_phase(pl);
-  if (pl->cg == 1) {
+  {
     // Large batches: the decode GEMM runs TRANSPOSED -- P[b][48] = h[b][:] . W5^T with the activations as an
     // MN-major A operand (128 poses per tile) and the 48 x 1024 weight as the K-major B operand.  With rows =
     // output features only 48 of the 128 accumulator lanes (1.5 of the 4 epilogue warps) carry data and every
     // prediction / target access is a 4-byte access at a 192-byte stride; with rows = poses each lane owns
     // one pose: 192 contiguous bytes of target in, 192 contiguous bytes of prediction out.
     if (add_gemm(pl, u.h_fm[4], 1, u.W[5], 0, pl->B, kDout, kHidden, kDout, EPI_DECODE_T, a)) return 1;
-  } else {
-    if (add_gemm(pl, u.W[5], 0, u.h_fm[4], 1, kDout, pl->B, kHidden, tile_bn(pl, pl->B), EPI_DECODE, a)) return 1;
   }
   if (end_phase(pl)) return 1;
   return 0;
@@ -869,11 +867,11 @@ int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
   pl->d = *desc;
   pl->B = desc->batch; pl->P = desc->precision; pl->kind = desc->kind;
   pl->large = pl->B > (pl->P == 1 ? 256 : 128);
-  // B200_CG=2 runs large-batch plans on CTA pairs (tcgen05 cta_group::2: M = 256 per MMA, each CTA loads half
-  // of the B tile).  Measured at B = 65536 it is no faster on the K = 1024 phases -- they are bound by the
-  // epilogue and TMA issue rate, not by operand bytes -- and slower on the 48-row decode layer, so single-CTA
-  // MMAs stay the default.
-  pl->cg = (pl->large && getenv("B200_CG") && atoi(getenv("B200_CG")) == 2) ? 2 : 1;
+  // Large-batch plans run on CTA pairs (tcgen05 cta_group::2: clusters of two CTAs share every MMA, M = 256, each
+  // CTA loads its 128 rows of A and HALF of the B tile): 32 KB instead of 48 KB per k-block go through each SM's
+  // shared memory, whose bandwidth -- TMA fill + tensor-core operand reads -- bounds the single-CTA 128 x 256 tile
+  // (DESIGN.md section 8).  B200_CG=1 keeps single-CTA MMAs (A/B comparison, parity-tested as well).
+  pl->cg = (pl->large && !(getenv("B200_CG") && atoi(getenv("B200_CG")) == 1)) ? 2 : 1;
   int dev = 0;
   cudaGetDevice(&dev);
   pl->sms = 148;

@@ -354,10 +354,10 @@ def test_fused_train_step(cuda_lib, precision, batch):
 
 
 @pytest.mark.parametrize("precision,batch", [("bf16", 1000), ("fp32", 300), ("bf16", 4096)])
-def test_fused_train_step_cta_pairs(cuda_lib, monkeypatch, precision, batch):
-    """The same iteration through the cta_group::2 build of the kernel (csrc/mega_pair.cu: clusters of two CTAs
-    share every MMA, M = 256; opt-in with B200_CG=2, read when the plan is created)."""
-    monkeypatch.setenv("B200_CG", "2")
+def test_fused_train_step_single_cta_mma(cuda_lib, monkeypatch, precision, batch):
+    """Large-batch plans run on CTA pairs by default (csrc/mega_pair.cu: tcgen05 cta_group::2, M = 256); B200_CG=1
+    (read when the plan is created) selects the single-CTA build of the same kernel -- same iteration, same oracle."""
+    monkeypatch.setenv("B200_CG", "1")
     test_fused_train_step(cuda_lib, precision, batch)
 
 
