@@ -21,6 +21,7 @@
 
 namespace b200 {
 cudaError_t launch_mega(const MegaParams& p, int grid, bool cooperative, cudaStream_t stream, int cg);
+int mega_pair_max_clusters(int grid);
 int mega_ring_bytes();
 struct EvalParams {
   const float* pred; const float* gt; const float* mean; const float* stddev; const int32_t* action;
@@ -876,6 +877,8 @@ int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
   cudaGetDevice(&dev);
   pl->sms = 148;
   cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, dev);
+  // pairs need one resident cluster per two SMs under the cooperative launch; otherwise the single-CTA build
+  if (pl->cg == 2 && mega_pair_max_clusters(pl->sms) < pl->sms / 2) pl->cg = 1;
   Carver c(desc->workspace);
   carve(c, pl->u, pl->B, pl->P, pl->kind);
   if (build_plan(pl)) { delete pl; return 1; }
