@@ -1,5 +1,8 @@
 """A handful of fused training iterations (ncu target; not a pytest module):
-python tests/gpu_onestep.py [fp32|bf16] [batch] [iters]"""
+python tests/gpu_onestep.py [fp32|bf16] [batch] [iters]
+
+Under ncu, large batches need B200_CG=1 in the environment: ncu cannot replay the cooperative cluster launch of
+the CTA-pair build (LaunchFailed)."""
 import os
 import sys
 import warnings
