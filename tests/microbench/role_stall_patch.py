@@ -1,6 +1,17 @@
-"""Temporary diagnostic patch (not committed): role stall accounting + knobs to skip TMA / MMA / epilogue."""
-import shutil, sys
-d='/root/repo/bilinear_b200/csrc/'
+"""Diagnostic patch of csrc/ (apply, build, measure, undo -- never commit the patched sources): the producer /
+MMA / epilogue roles count the cycles they wait on each mbarrier, and B200_DBG bits skip the TMA loads (1), the
+MMAs (2) or the epilogue body (4).
+
+    python tests/microbench/role_stall_patch.py [--csrc DIR]        apply (keeps *.orig copies)
+    python tests/microbench/role_stall_patch.py [--csrc DIR] undo   restore
+
+tests/test_abi.py applies it to a scratch copy of csrc/ so that it cannot silently fall behind the sources."""
+import os, shutil, sys
+d = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'bilinear_b200', 'csrc') + os.sep
+if '--csrc' in sys.argv:
+    i = sys.argv.index('--csrc')
+    d = os.path.join(sys.argv[i + 1], '')
+    del sys.argv[i:i + 2]
 if sys.argv[1:] == ['undo']:
     for f in ['mega.cu','api.cu','jobs.h']: shutil.copy(d+f+'.orig', d+f)
     sys.exit(0)
