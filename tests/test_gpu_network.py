@@ -112,65 +112,6 @@ TOL_Y = {"fp32": 2e-5, "bf16": 3e-2}
 TOL_SAME = {"fp32": 1e-5, "bf16": 1e-2}
 
 
-def adopt_relu_decisions(net, masks, batch, tol_y):
-    """ReLU's derivative is discontinuous: take the CUDA path's own decisions (keep bits saved by the
-    forward) wherever they differ from the oracle's, after asserting that every such element has its
-    oracle BatchNorm output within `tol_y` of the kink (i.e. the decision is round-off either way)."""
-    from bilinear_b200.engine import get_engine
-    eng = get_engine(net)
-
-    def fn(cache):
-        out = []
-        for i, c in enumerate(cache["layers"]):
-            keep = eng.debug_keep_bits(i, batch).cpu()
-            m = masks[i].bool()
-            pos = torch.where(m, keep, c["pos"])
-            dis = pos != c["pos"]
-            if int(dis.sum()):
-                worst = float(c["y"].abs()[dis].max())
-                assert worst < tol_y, "layer %d: %d ReLU decisions differ, |y| up to %g" % (i, int(dis.sum()), worst)
-            out.append(pos)
-        return out
-    return fn
-
-
-def grad_errors(gv, grads):
-    gn = float(bo.total_grad_norm(grads))
-    out = {}
-    for name in bo.param_names():
-        if name in ZERO_GRAD:
-            out[name] = float((gv[name].double().cpu() - grads[name]).norm()) / gn
-        else:
-            out[name] = rel_l2(gv[name], grads[name])
-    return out
-
-
-def adam_state_dict(st):
-    """torch.optim.Adam state_dict carrying the oracle's moments (checkpoint format, train_bilinear.py:92-104)."""
-    names = bo.param_names()
-    return {
-        "state": {i: {"step": torch.tensor(float(st.adam_step)), "exp_avg": st.m[n].float().clone(),
-                      "exp_avg_sq": st.v[n].float().clone()} for i, n in enumerate(names)},
-        "param_groups": [{"lr": 1e-3, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False,
-                          "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
-                          "fused": None, "decoupled_weight_decay": False, "params": list(range(len(names)))}],
-    }
-
-
-def rounding_for(precision, batch):
-    return bo.EXACT if precision == "fp32" else bo.Rounding.bf16(large_batch=batch > 256)
-
-
-# ReLU-kink tolerance on the oracle's BatchNorm output (O(1) scale): fp32 mode agrees to ~1e-6.  The bf16
-# path against the bf16 restatement: an fp32-vs-fp64 accumulation difference of 1e-6 flips the bf16
-# rounding of ~3e-4 of the activations by one ulp (4e-3 relative); those perturb the next layer's
-# pre-activations by ~5e-4, which re-rounds ~10% of ITS outputs, and so on -- two correct bf16
-# evaluations decorrelate to a few 1e-3 within five layers (measured 4-5e-3 on gradients)
-TOL_Y = {"fp32": 2e-5, "bf16": 3e-2}
-# CUDA vs the restatement evaluated with the SAME operand rounding
-TOL_SAME = {"fp32": 1e-5, "bf16": 1e-2}
-
-
 # ------------------------------------------------------------------------------------------ eval mode
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("batch", [1, 2, 64, 257, 1000, 4096])
