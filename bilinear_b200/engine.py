@@ -315,6 +315,9 @@ class Engine:
                              % str(torch.Size([B, 1024])))
         pl = self.plan(B, PLAN_TRAIN)
         t = self._train_args(x, y, None, B)
+        # every rank draws ITS OWN dropout bits: the Philox key carries the rank (the counter carries step,
+        # layer, feature and local batch word), so row i of two shards never shares a keep mask
+        t.seed = (self.seed + 0x9E3779B97F4A7C15 * (self.comm.rank + 1)) & 0xFFFFFFFFFFFFFFFF
         t.loss_out = self.scalars[0:1].data_ptr()
         t.gnorm_out = self.scalars[1:2].data_ptr()
         ep = C.c_uint32(self.comm.epoch)

@@ -134,6 +134,10 @@ def _enable_data_parallel(self, group=None):
     if not dev.type == "cuda":
         raise RuntimeError("bilinear_b200 runs on CUDA (sm_100a) only: move the module to a CUDA device first")
     eng.attach_comm(parallel.PeerComm(dev, group))
+    # Replicas must start identical and stay identical (what DistributedDataParallel does in its constructor):
+    # rank 0's parameters, BatchNorm buffers and Philox base seed go to every rank, so a per-rank torch seed
+    # cannot silently fork the model.  The dropout stream itself is keyed per rank (Engine.train_step_dp).
+    parallel.broadcast_module_state(self, eng, group)
     return self
 
 

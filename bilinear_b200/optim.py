@@ -16,6 +16,7 @@ class FusedAdam(torch.optim.Adam):
         super().__init__(module.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False)
         self._module = module
         self._t = 0          # Adam's per-parameter step count (identical for all 22 tensors)
+        self._adopted_for = None   # address of the flat moment buffer self.state was last checked against
 
     # ------------------------------------------------------------------ helpers
     def _hyper(self):
@@ -30,6 +31,33 @@ class FusedAdam(torch.optim.Adam):
         for p, mi, vi in zip(self._module.parameters(), m, v):
             self.state[p] = {"step": torch.tensor(float(self._t)), "exp_avg": mi, "exp_avg_sq": vi}
 
+    def _sync_foreign_state(self):
+        """Moments that are NOT views of the engine's flat buffers -- a checkpoint loaded while the module
+        was still on the CPU (load(device=cpu, parameter_dir=...) followed by .to('cuda')), or buffers
+        re-created after a device change -- are copied in before the kernel reads them.  Without this the
+        kernel would run Adam on zeroed moments with step count > 0 and the next state_dict() would
+        overwrite what was loaded."""
+        if self._t <= 0 or not self.state:
+            return
+        eng = get_engine(self._module)
+        eng.ensure_flat()
+        if self._adopted_for == eng.flat_m.data_ptr():     # hot path: one integer comparison per step
+            return
+        m, v = eng.state_views()
+        foreign = False
+        with torch.no_grad():
+            for p, mi, vi in zip(self._module.parameters(), m, v):
+                st = self.state.get(p)
+                if not st or "exp_avg" not in st:
+                    continue
+                if st["exp_avg"].data_ptr() != mi.data_ptr() or st["exp_avg_sq"].data_ptr() != vi.data_ptr():
+                    mi.copy_(st["exp_avg"].to(mi.device).reshape(mi.shape))
+                    vi.copy_(st["exp_avg_sq"].to(vi.device).reshape(vi.shape))
+                    foreign = True
+        if foreign:
+            self._adopt_state()
+        self._adopted_for = eng.flat_m.data_ptr()
+
     # ------------------------------------------------------------------ torch.optim API
     @torch.no_grad()
     def step(self, closure=None):
@@ -39,6 +67,7 @@ class FusedAdam(torch.optim.Adam):
             raise RuntimeError("closures are not supported")
         eng = get_engine(self._module)
         eng.ensure_flat()
+        self._sync_foreign_state()
         views = eng.grad_views()
         for p, v in zip(self._module.parameters(), views):
             if p.grad is None:
@@ -53,6 +82,7 @@ class FusedAdam(torch.optim.Adam):
     def fused_step(self, module, x, y, max_norm=1.0, update=True, grad_scale=1.0):
         assert module is self._module
         eng = get_engine(module)
+        self._sync_foreign_state()
         lr, betas, eps = self._hyper()
         if update:
             self._t += 1
@@ -64,6 +94,7 @@ class FusedAdam(torch.optim.Adam):
     def fused_step_dp(self, module, x, y, max_norm=1.0, world=1):
         assert module is self._module
         eng = get_engine(module)
+        self._sync_foreign_state()
         lr, betas, eps = self._hyper()
         self._t += 1
         out = eng.train_step_dp(x, y, eng.adam_args(lr, self._t, max_norm, 1.0 / world, betas, eps))
@@ -74,6 +105,7 @@ class FusedAdam(torch.optim.Adam):
     def fused_step_host(self, module, x_host, y_host, max_norm=1.0, update=True, grad_scale=1.0):
         assert module is self._module
         eng = get_engine(module)
+        self._sync_foreign_state()
         lr, betas, eps = self._hyper()
         if update:
             self._t += 1
@@ -86,6 +118,7 @@ class FusedAdam(torch.optim.Adam):
     def finish_step(self, max_norm=1.0, grad_scale=1.0):
         """Data parallel: clip + Adam on the (already all-reduced) flat gradient buffer."""
         eng = get_engine(self._module)
+        self._sync_foreign_state()
         lr, betas, eps = self._hyper()
         self._t += 1
         out = eng.adam_step(eng.adam_args(lr, self._t, max_norm, grad_scale, betas, eps))
@@ -94,12 +127,16 @@ class FusedAdam(torch.optim.Adam):
         return out
 
     def state_dict(self):
-        if self._t > 0:
+        # on the device the moments live in the engine's flat buffers; a module still on the CPU (checkpoint
+        # loaded, not yet moved) holds them as ordinary torch.optim.Adam state -- nothing to adopt there
+        if self._t > 0 and next(self._module.parameters()).is_cuda:
+            self._sync_foreign_state()
             self._adopt_state()
         return super().state_dict()
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
+        self._adopted_for = None
         params = list(self._module.parameters())
         steps = [float(self.state[p]["step"]) for p in params if p in self.state and "step" in self.state[p]]
         self._t = int(steps[0]) if steps else 0

@@ -142,6 +142,29 @@ class PeerComm:
             self.own = None
 
 
+def broadcast_module_state(module, engine, group=None, src=0):
+    """Rank `src`'s parameters, buffers and dropout base seed -> every rank (no-op for a world of one)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
+    dev = next(module.parameters()).device
+    seed = torch.tensor([engine.seed & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=dev)
+    dist.broadcast(seed, src=src, group=group)
+    engine.seed = int(seed.item())
+    engine.note_external_param_write()
+
+
+def broadcast_int(value, device, group=None, src=0):
+    """One Python int from rank `src` to all ranks (e.g. the seed of the data permutation)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return int(value)
+    t = torch.tensor([int(value) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=device)
+    dist.broadcast(t, src=src, group=group)
+    return int(t.item())
+
+
 def combine_action_sums(sums, psums, counts, group=None):
     """valid_bilinear.py:61-70 across ranks: per-action fp64 sums and int64 counts add up."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -24,10 +24,23 @@ def make_raw(n, seed):
             "scale": [1.0 + 0.01 * i for i in range(n)], "image": images}
 
 
-def write_dataset(root, n_train=40, n_valid=24):
+def make_raw_detected(n, seed, protocol):
+    """{task}_SH.bin / {task}_SH+FT.bin (H36M/data.py:33; written by `SH preprocess.ipynb` cells 7-13): the SAME
+    poses and image names as the GT file, with the 2D joints replaced by stacked-hourglass detections -- here
+    the GT joints plus detector noise (SH+FT: the fine-tuned detector, less noise)."""
+    raw = make_raw(n, seed)
+    rng = np.random.RandomState(1000 + seed + (0 if protocol == "SH" else 1))
+    sigma = 12.0 if protocol == "SH" else 6.0
+    raw["part"] = [p + rng.randn(17, 2) * sigma for p in raw["part"]]
+    return raw
+
+
+def write_dataset(root, n_train=40, n_valid=24, protocols=("GT",)):
     d = os.path.join(root, "data", "Human3.6M")
     os.makedirs(d, exist_ok=True)
-    for task, n, seed in (("train", n_train, 1), ("valid", n_valid, 2)):
-        with open(os.path.join(d, "%s_GT.bin" % task), "wb") as f:
-            pickle.dump(make_raw(n, seed), f)
+    for protocol in protocols:
+        for task, n, seed in (("train", n_train, 1), ("valid", n_valid, 2)):
+            raw = make_raw(n, seed) if protocol == "GT" else make_raw_detected(n, seed, protocol)
+            with open(os.path.join(d, "%s_%s.bin" % (task, protocol)), "wb") as f:
+                pickle.dump(raw, f)
     return d

@@ -26,9 +26,13 @@ import H36M  # noqa: E402
 
 out = {}
 with tempfile.TemporaryDirectory() as tmp:
-    d = _h36m_synth.write_dataset(tmp)
-    for task in (H36M.Task.Train, H36M.Task.Valid):
-        ds = H36M.Dataset(data_dir=d, task=task, protocol=H36M.Protocol.GT)
+    d = _h36m_synth.write_dataset(tmp, protocols=("GT", "SH", "SH+FT"))
+    # GT entries keep their historic keys ("train/part"); the detector protocols (H36M/protocol.py:3-4) are
+    # stored under "SH/train/part", "SH+FT/train/part", ...
+    for protocol, task in [(p, t) for p in (H36M.Protocol.GT, H36M.Protocol.SH, H36M.Protocol.SH_FT)
+                           for t in (H36M.Task.Train, H36M.Task.Valid)]:
+        ds = H36M.Dataset(data_dir=d, task=task, protocol=protocol)
+        prefix = task if protocol == H36M.Protocol.GT else protocol + "/" + task
         parts, Ss, acts = [], [], []
         for i in range(len(ds)):
             sample, image, heatmap, action = ds[i]
@@ -38,10 +42,10 @@ with tempfile.TemporaryDirectory() as tmp:
             acts.append(action)
             mean = sample[H36M.Annotation.Mean_Of + H36M.Annotation.S]
             std = sample[H36M.Annotation.Stddev_Of + H36M.Annotation.S]
-        out[task + "/part"] = np.stack(parts)
-        out[task + "/S"] = np.stack(Ss)
-        out[task + "/action"] = np.array(acts)
-        out[task + "/mean_S"] = mean
-        out[task + "/stddev_S"] = std
+        out[prefix + "/part"] = np.stack(parts)
+        out[prefix + "/S"] = np.stack(Ss)
+        out[prefix + "/action"] = np.array(acts)
+        out[prefix + "/mean_S"] = mean
+        out[prefix + "/stddev_S"] = std
 np.savez_compressed(os.path.join(HERE, "h36m_golden.npz"), **out)
 print({k: v.shape for k, v in out.items()})

@@ -101,3 +101,35 @@ def test_shards_partition_the_poses():
         assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
         assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
         assert [h36m.shard(n, k, w) for k in range(w)] == r
+
+
+# ------------------------------------------------------------------------------------------ detector protocols
+@pytest.fixture(scope="module")
+def data_dir_all(tmp_path_factory):
+    return _h36m_synth.write_dataset(str(tmp_path_factory.mktemp("h36m_all")), protocols=("GT", "SH", "SH+FT"))
+
+
+@pytest.mark.parametrize("protocol", [h36m.Protocol.SH, h36m.Protocol.SH_FT])
+@pytest.mark.parametrize("task", ["train", "valid"])
+def test_detector_protocols_are_bit_identical_to_reference(gold, data_dir_all, protocol, task):
+    """H36M/protocol.py:3-4, H36M/data.py:33: `Protocol.SH` / `Protocol.SH_FT` read {task}_SH.bin / {task}_SH+FT.bin --
+    the same poses with stacked-hourglass 2D detections in place of the ground-truth joints.  Golden: the UNMODIFIED
+    H36M.Dataset on the same synthetic pickles (tests/golden/make_h36m_golden.py)."""
+    ds = h36m.PoseDataset(data_dir_all, task, protocol)
+    pre = protocol + "/" + task
+    assert np.array_equal(ds.part.numpy(), gold[pre + "/part"])
+    assert np.array_equal(ds.S.numpy(), gold[pre + "/S"])
+    assert np.array_equal(ds.mean_S.numpy(), gold[protocol + "/train/mean_S"])
+    assert np.array_equal(ds.stddev_S.numpy(), gold[protocol + "/train/stddev_S"])
+    assert list(ds.actions) == list(gold[pre + "/action"])
+    # the 3D side is the GT file's; only the 2D inputs (and therefore their z-score statistics) differ
+    gt = h36m.PoseDataset(data_dir_all, task, h36m.Protocol.GT)
+    assert np.array_equal(ds.S.numpy(), gt.S.numpy()) and not np.array_equal(ds.part.numpy(), gt.part.numpy())
+
+
+def test_protocol_selects_the_file(tmp_path):
+    d = _h36m_synth.write_dataset(str(tmp_path))            # GT files only
+    with pytest.raises(FileNotFoundError):
+        h36m.PoseDataset(d, "train", h36m.Protocol.SH)      # data/Human3.6M/train_SH.bin (H36M/data.py:33)
+    with pytest.raises(AssertionError):
+        h36m.PoseDataset(d, "train", "SH_FT")               # not a Protocol value (H36M/data.py:22)

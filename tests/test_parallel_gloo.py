@@ -60,6 +60,29 @@ def _worker(rank, world, port, out_dir):
     assert torch.equal(sums, full) and torch.equal(psums, 2 * full) and int(cnt.sum()) == n
     assert parallel.max_over_ranks(10.0 + rank, torch.device("cpu")) == 10.0 + world - 1
 
+    # ---- replicas start identical: rank 0's parameters / buffers / dropout base seed reach every rank, and the
+    # data permutation seed is rank 0's, even when the processes were seeded differently
+    import torch.nn as nn
+
+    class _Eng:
+        seed = 1000 + rank
+        bumped = 0
+
+        def note_external_param_write(self):
+            self.bumped += 1
+    torch.manual_seed(50 + rank)                     # per-rank seeding: the replicas differ before the broadcast
+    toy = nn.Sequential(nn.Linear(4, 3), nn.BatchNorm1d(3))
+    toy[1].running_mean.fill_(float(rank))
+    eng = _Eng()
+    parallel.broadcast_module_state(toy, eng)
+    torch.manual_seed(50)
+    ref_toy = nn.Sequential(nn.Linear(4, 3), nn.BatchNorm1d(3))
+    assert torch.equal(toy[0].weight, ref_toy[0].weight) and float(toy[1].running_mean[0]) == 0.0
+    assert eng.seed == 1000 and eng.bumped == 1
+    assert parallel.broadcast_int(777 + rank, torch.device("cpu")) == 777
+    # ragged tail: train_bilinear.py drops a global batch that leaves some rank with fewer than two rows
+    assert [n_tail < 2 * world for n_tail in (1, 3, 4, 5)] == [True, True, False, False]
+
     # ---- data-parallel step == "reference per shard, gradients averaged" (local BatchNorm), identical on all ranks
     torch.manual_seed(0)
     sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -77,7 +77,8 @@ def main(cfg=None, save_root='save'):
     if world > 1:
         # one process per GPU: peer-mapped gradient buffers for the in-kernel all-reduce
         bilinear.enable_data_parallel()
-    gen = torch.Generator().manual_seed(int(torch.initial_seed()) & 0x7fffffff)   # same permutation on every rank
+    # the SAME permutation on every rank: rank 0's seed is broadcast (per-rank seeding must not fork the shards)
+    gen = torch.Generator().manual_seed(parallel.broadcast_int(int(torch.initial_seed()) & 0x7fffffff, device))
     global_batch = cfg.batch_size * world
     steps_per_epoch = (len(data) + global_batch - 1) // global_batch
     ring = torch.zeros(steps_per_epoch, dtype=torch.float32, device=device)
@@ -89,6 +90,14 @@ def main(cfg=None, save_root='save'):
         k = 0
         for part, S, _ in data.batches(global_batch, shuffle=True, generator=gen):
             if world > 1:       # this rank's rows of the global batch
+                if part.shape[0] < 2 * world:
+                    # ragged tail with fewer than two rows for some rank: BatchNorm cannot train on one row
+                    # (the single-GPU reference fails the same way at N % 64 == 1).  Every rank sees the same
+                    # shape, so every rank drops the batch -- none is left waiting in the gradient exchange.
+                    if rank == 0:
+                        logger.info('tail batch of {n} poses dropped ({w} ranks need 2 rows each)'.format(
+                            n=part.shape[0], w=world))
+                    continue
                 lo, hi = parallel.shard_range(part.shape[0], rank, world)
                 part, S = part[lo:hi], S[lo:hi]
 
