@@ -1,20 +1,26 @@
-"""Benchmark of the pose-lifting hot path on B200 (contract: see README / DESIGN.md section "Measurement").
+"""Benchmark of the pose-lifting hot path on B200 (contract: DESIGN.md section "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train_b64|train_b65536|infer_10m|eval_1m]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train_b65536|train_b64]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+    python bench.py --impl reference ...   # the UNMODIFIED reference module on the box's host cores (CPU)
+    python bench.py --impl torch_gpu ...   # the UNMODIFIED reference module on the same B200 (torch eager / CUDA graph)
 
-Headline workload (BASELINE.json configs[1]): one training iteration of train_bilinear.py:75-83 at batch
-64 per GPU -- zero_grad, forward, MSELoss, backward, clip_grad_norm_(1), Adam -- as ONE persistent
-sm_100a kernel, fp32-parity mode.  A "step" is one such iteration over one batch of synthetic H36M-shaped
-data (x ~ N(0,1) [64,32], y ~ N(0,1) [64,48], random-init weights, in-kernel Philox dropout).  `value` is
-whole-job poses/s with the inputs resident in HBM; `e2e` is the same through the public nn.Module API with
-pinned HOST inputs copied in and the loss read back every step.  The other BASELINE configs (large-batch
-bf16 training, 10M-pose inference, 1M-pose MPJPE/P-MPJPE) are measured in the same run and reported
-under "also", each with its own roofline.
+Headline workload (BASELINE.json configs[2], the largest single-GPU configuration and the one the north-star
+targets are quoted on): one training iteration of train_bilinear.py:75-83 -- zero_grad, forward, MSELoss,
+backward, clip_grad_norm_(1), Adam -- at batch 65 536 PER GPU in bf16 mode, as one persistent sm_100a kernel;
+data parallel (N > 1) with the gradient all-reduce inside that kernel.  A "step" is one such iteration over one
+batch of synthetic H36M-shaped data (x ~ N(0,1) [B,32], y ~ N(0,1) [B,48], random-init weights, in-kernel Philox
+dropout).  `value` is whole-job poses/s with the inputs resident in HBM (CUDA events on the launching stream);
+`e2e` is the same through the public nn.Module API with pinned HOST batches: every step copies its own inputs
+host -> device (bilinear_b200.feed.PinnedPrefetcher keeps that copy one step ahead on a side stream) and reads
+the loss back.  The other BASELINE configs -- the batch-64 persistent-kernel step (configs[1]), 10 M-pose
+inference, 1 M-pose MPJPE / P-MPJPE, and at N > 1 the strong-scaling row (65 536 GLOBAL) -- are measured in the
+same run and reported compactly under "also"; "torch_gpu" holds the reference's own GPU path (the unmodified
+module under torch on the same B200) for the two training configs.
 
-One JSON line on stdout (rank 0).  Nothing here reads /root/reference.
+One JSON line on stdout (rank 0).  Nothing here reads /root/reference: the reference module comes from
+baseline/_ref (staged by __graft_entry__.build()).
 """
 import argparse
 import json
@@ -34,12 +40,15 @@ FLOP_PER_POSE_FWD = 8552448
 PARAM_NUMEL = 4291632
 ADAM_BYTES_PER_STEP = 6 * 4 * PARAM_NUMEL   # p, m, v read + written (SURVEY.md section 8(d), B=64 row)
 SPACER_CYCLES = 600_000                     # ~0.3 ms at 1.9 GHz
-EVAL_BYTES_PER_POSE = 384                   # 2 x 16 x 3 x 4 read (+ 4 written when per-pose output is kept)
+EVAL_BYTES_PER_POSE = 384                   # 2 x 16 x 3 x 4 bytes read per pose
+LARGE_BATCH = 65536
+CPU_SAMPLE_ROWS = 8192                      # rows of the 65 536-row step the CPU arm times per step (bounded sample)
+NCU_TRAFFIC = {"train_b65536": "r2_train_step_b65536_bf16_ncu.csv", "train_b64": "r1p_train_step_b64_fp32_ncu_full.csv"}
 
 
 def ncu_traffic(name):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` summary under profiles/ (bytes), or None."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+    summary under profiles/ (bytes), or None."""
     path = os.path.join(ROOT, "profiles", name)
     try:
         tot = 0.0
@@ -77,7 +86,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -112,9 +121,11 @@ class ClockSampler:
                     reasons.add(n)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        # median over the samples taken UNDER LOAD (power well above idle); all samples if none qualifies
+        busy = [s for s, p in zip(sm, pw) if p > 400.0] or sm
+        busy.sort()
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "samples_under_load": len(busy), "reasons": sorted(reasons)}
 
 
 def make_model(precision, device, seed=0):
@@ -134,7 +145,7 @@ def lr_for(step):
 
 
 class TrainLoop:
-    """The hot loop of train_bilinear.py:60-90 on device-resident synthetic batches."""
+    """The hot loop of train_bilinear.py:60-90 on synthetic batches."""
 
     def __init__(self, precision, batch, device, world, nbatches):
         import torch
@@ -151,7 +162,7 @@ class TrainLoop:
         # pinned host batches as a DataLoader(pin_memory=True) delivers them; x and y of one batch share a
         # pinned block [x | y] so that the library can move them with a single copy
         self.hx, self.hy = [], []
-        for x, y in zip(self.xs[:8], self.ys[:8]):
+        for x, y in zip(self.xs[:4], self.ys[:4]):
             blk = torch.empty(batch * 80, dtype=torch.float32).pin_memory()
             hx, hy = blk[:batch * 32].view(batch, 32), blk[batch * 32:].view(batch, 48)
             hx.copy_(x.cpu()); hy.copy_(y.cpu())
@@ -180,20 +191,37 @@ class TrainLoop:
         self.step += 1
         return out
 
-    def one_e2e(self):
-        """train_bilinear.py:62-88 through the public API with pinned HOST batches: H2D of x and y, the step,
-        and the loss read back (train_bilinear.py:88) every iteration."""
+    def e2e_small(self):
+        """train_bilinear.py:62-88 at batch 64 on one GPU: H2D of x and y, the step and the loss read-back are ONE
+        library call (BilinearUnit.train_step_host)."""
         k = self.i % len(self.hx)
-        if self.world == 1:
-            self._lr()
-            self.i += 1
-            loss, _ = self.net.train_step_host(self.opt, self.hx[k], self.hy[k], max_norm=1.0)
-            self.step += 1
-            return loss
-        x = self.hx[k].to(self.device, non_blocking=True)
-        y = self.hy[k].to(self.device, non_blocking=True)
-        loss, _ = self.one(x, y)
-        return float(loss.item())
+        self._lr()
+        self.i += 1
+        loss, _ = self.net.train_step_host(self.opt, self.hx[k], self.hy[k], max_norm=1.0)
+        self.step += 1
+        return loss
+
+    def e2e_run(self, steps):
+        """`steps` iterations fed from pinned HOST batches: each step's inputs are copied host -> device inside
+        the timed region (one step ahead, on a side stream) and each step's loss is read back on the host --
+        like train_bilinear.py:88 reads loss.item() -- one step late, so that the read never drains the queue."""
+        from bilinear_b200.feed import PinnedPrefetcher
+        torch = self.torch
+        host = ((self.hx[i % len(self.hx)], self.hy[i % len(self.hy)]) for i in range(steps))
+        feed = PinnedPrefetcher(host, self.device)
+        ring = torch.zeros(2, dtype=torch.float32).pin_memory()
+        evs = [torch.cuda.Event(), torch.cuda.Event()]
+        total = 0.0
+        for i, (x, y) in enumerate(feed):
+            loss, _ = self.one(x, y)
+            ring[i & 1].copy_(loss, non_blocking=True)      # 4-byte D2H of this step's loss
+            evs[i & 1].record()
+            if i > 0:
+                evs[(i - 1) & 1].synchronize()
+                total += float(ring[(i - 1) & 1])
+        evs[(steps - 1) & 1].synchronize()
+        total += float(ring[(steps - 1) & 1])
+        return total, feed.h2d_bytes // max(steps, 1)
 
 
 class L2Flusher:
@@ -207,7 +235,7 @@ class L2Flusher:
         self.buf.fill_(float(self.k))
 
 
-def timed_steps(torch, parallel, fn, steps, flusher, device):
+def timed_steps(torch, parallel, fn, steps, flusher, device, spacer=True):
     """Sum of per-step CUDA-event times (ms) on the launching stream, L2 flushed between steps (outside
     the event pairs); barrier + synchronize on both sides; max over ranks."""
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -219,7 +247,8 @@ def timed_steps(torch, parallel, fn, steps, flusher, device):
         # ~0.3 ms device-side spacer: the host enqueues the start event, the step and the stop event while
         # the GPU is still busy, so the event pair measures the step on the device and not the Python /
         # ctypes launch path (that path is what `e2e` measures, on the wall clock)
-        torch.cuda._sleep(SPACER_CYCLES)
+        if spacer:
+            torch.cuda._sleep(SPACER_CYCLES)
         a.record()
         fn()
         b.record()
@@ -229,55 +258,79 @@ def timed_steps(torch, parallel, fn, steps, flusher, device):
     return parallel.max_over_ranks(ms, device)
 
 
-def timed_wall(torch, parallel, fn, steps, device):
+def timed_block(torch, parallel, fn, steps, device):
+    """K steps back to back between ONE pair of CUDA events (ms): what a long-running job sees -- no spacer,
+    no flush (the large-batch step streams > 8 GB through a 126 MB L2 by itself)."""
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    parallel.barrier()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    return parallel.max_over_ranks(a.elapsed_time(b), device)
+
+
+def timed_wall(torch, parallel, fn, device):
     parallel.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        fn()
+    out = fn()
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) * 1e3
     parallel.barrier()
-    return parallel.max_over_ranks(ms, device)
+    return parallel.max_over_ranks(ms, device), out
 
 
 # ------------------------------------------------------------------------------------------------ workloads
-def bench_train(args, precision, batch, steps, warmup, device, world, peaks, flush=True, with_e2e=True):
+def bench_train(precision, batch, steps, warmup, device, world, peaks, with_e2e=True):
     import torch
     from bilinear_b200 import _lib, parallel
-    loop = TrainLoop(precision, batch, device, world, nbatches=(64 if batch <= 4096 else 3))
+    small = batch <= 4096
+    loop = TrainLoop(precision, batch, device, world, nbatches=(64 if small else 3))
     for _ in range(max(warmup, 3)):
         loop.one()
-    flusher = L2Flusher(device) if flush else None
     n0 = _lib.lib().b200_launch_count()
-    ms = timed_steps(torch, parallel, loop.one, steps, flusher, device)
+    if small:
+        flusher = L2Flusher(device)
+        ms = timed_steps(torch, parallel, loop.one, steps, flusher, device)
+    else:
+        ms = timed_block(torch, parallel, loop.one, steps, device)
     launches = _lib.lib().b200_launch_count() - n0
     ms_step = ms / steps
     poses = batch * world
     res = dict(value=poses / (ms_step * 1e-3), ms_per_step=ms_step, launches=launches)
-    if flush:   # steady state, parameters L2-resident (no flush) -- reported beside the flushed number
-        ms_warm = timed_steps(torch, parallel, loop.one, steps, None, device)
-        res["ms_per_step_warm_l2"] = ms_warm / steps
+    if small:   # steady state, parameters L2-resident (no flush) -- reported beside the flushed number
+        res["ms_per_step_warm_l2"] = timed_steps(torch, parallel, loop.one, steps, None, device) / steps
     if with_e2e:
-        for _ in range(3):
-            loop.one_e2e()
-        ms_e = timed_wall(torch, parallel, loop.one_e2e, steps, device)
-        res["e2e"] = dict(value=poses / (ms_e / steps * 1e-3), unit="poses/s", h2d_bytes_per_step=batch * (32 + 48) * 4,
+        if small and world == 1:
+            for _ in range(3):
+                loop.e2e_small()
+            ms_e, _ = timed_wall(torch, parallel, lambda: [loop.e2e_small() for _ in range(steps)], device)
+            h2d = batch * 80 * 4
+        else:
+            loop.e2e_run(3)
+            ms_e, (_, h2d) = timed_wall(torch, parallel, lambda: loop.e2e_run(steps), device)
+        res["e2e"] = dict(value=poses / (ms_e / steps * 1e-3), unit="poses/s", h2d_bytes_per_step=int(h2d),
                           d2h_bytes_per_step=4, ms_per_step=ms_e / steps)
     if batch <= 256:
         ach = ADAM_BYTES_PER_STEP / (ms_step * 1e-3) / 1e9
         res["roofline"] = dict(bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"],
-                               traffic=ncu_traffic("r1p_train_step_b64_fp32_ncu_full.csv") if precision == "fp32" else None,
-                               traffic_source="profiles/r1p_train_step_b64_fp32_ncu_full.csv (bytes per launch)",
+                               traffic=ncu_traffic(NCU_TRAFFIC["train_b64"]) if precision == "fp32" else None,
                                peak_source=peaks["source"],
                                algorithmic="6 x 4 B x 4 291 632 parameters (Adam p,m,v read+write) per step")
     else:
         ach = FLOP_PER_POSE_TRAIN * batch / (ms_step * 1e-3) / 1e12
-        pk = peaks["bf16_sustained"]
-        res["roofline"] = dict(bound="tensor", achieved=ach, peak=pk, unit="TFLOP/s", frac=ach / pk,
-                               traffic=ncu_traffic("r1p_train_step_b65536_bf16_ncu_full.csv") if batch == 65536 else None,
-                               peak_source=peaks["source"] + " (sustained bf16 cuBLAS)",
-                               algorithmic="25 591 808 FLOP/pose x %d poses per step" % batch)
+        res["roofline"] = dict(bound="tensor", achieved=ach, peak=peaks["bf16"], unit="TFLOP/s", frac=ach / peaks["bf16"],
+                               frac_of_sustained=ach / peaks["bf16_sustained"],
+                               traffic=ncu_traffic(NCU_TRAFFIC["train_b65536"]) if batch == LARGE_BATCH else None,
+                               peak_source=peaks["source"] + " (cuBLAS bf16 8192^3: burst %.0f, sustained %.0f TFLOP/s)"
+                               % (peaks["bf16"], peaks["bf16_sustained"]),
+                               algorithmic="25 591 808 FLOP/pose x %d poses per step per GPU" % batch)
+    del loop
+    torch.cuda.empty_cache()
     return res
 
 
@@ -302,10 +355,12 @@ def bench_infer(total, chunk, precision, steps, warmup, device, rank, world, pea
         run()
     ms = timed_steps(torch, parallel, run, steps, None, device) / steps
     ach = FLOP_PER_POSE_FWD * n / (ms * 1e-3) / 1e12
-    pk = peaks["bf16_sustained"]
+    # fp32-parity mode issues six bf16 MMAs per product (3-way split operands): its ceiling is 1/6 of the bf16 peak
+    pk = peaks["bf16"] / (6.0 if precision == "fp32" else 1.0)
     return dict(workload="infer_%d_%s" % (total, precision), value=total / (ms * 1e-3), unit="poses/s", ms=ms,
-                chunk=chunk, l2="inputs (%.0f MB per rank) exceed L2" % (n * 128 / 1e6),
-                roofline=dict(bound="tensor", achieved=ach, peak=pk, unit="TFLOP/s", frac=ach / pk, traffic=None))
+                roofline=dict(bound="tensor", achieved=ach, peak=pk, unit="TFLOP/s", frac=ach / pk,
+                              note="fp32-parity mode: 6 bf16 MMAs per product, peak = bf16 burst / 6" if precision == "fp32"
+                              else "bf16 burst"))
 
 
 def bench_eval(total, steps, warmup, device, rank, world, peaks):
@@ -329,51 +384,154 @@ def bench_eval(total, steps, warmup, device, rank, world, peaks):
         for _ in range(max(warmup, 3)):
             fn()
         ms = timed_steps(torch, parallel, fn, steps, flusher, device) / steps
-        ach = (EVAL_BYTES_PER_POSE + (8 if name == "fused" else 4) + 4) * n / (ms * 1e-3) / 1e9
-        out[name] = dict(value=total / (ms * 1e-3), unit="poses/s", ms=ms,
-                         roofline=dict(bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s",
-                                       frac=ach / peaks["hbm"], traffic=None))
+        ach = EVAL_BYTES_PER_POSE * n / (ms * 1e-3) / 1e9        # 384 B/pose, nothing else counted
+        out[name] = dict(value=total / (ms * 1e-3), us=ms * 1e3, hbm_frac=ach / peaks["hbm"], gbs=ach)
     r = metrics.evaluate(pred, gt, mean, std, act, 15, joints=16)
     parallel.combine_action_sums(r.sum, r.psum, r.count)
     out["mpjpe_mm"], out["pmpjpe_mm"] = r.mpjpe, r.pmpjpe
-    out["workload"] = "eval_%d" % total
-    out["l2"] = "flushed between iterations"
+    out["workload"] = "eval_%d (MPJPE / P-MPJPE / both in one pass; 384 B per pose; L2 flushed between iterations)" % total
+    out["unit"] = "poses/s"
     return out
 
 
-# ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_train_sample(batch, seconds_budget, min_steps=3):
-    """The reference's CPU path for one training iteration (train_bilinear.py:75-83), restated by the
-    oracle port in float32 on all host threads.  Returns (poses/s, steps timed, threads)."""
+# ------------------------------------------------------------------------------------------------ reference arms
+def reference_module():
+    import baseline
+    return baseline.load_reference_module()
+
+
+def reference_step_fn(ref, device, batch, autocast=False, seed=0):
+    """The unmodified reference module + the literal sequence of train_bilinear.py:66-83 on synthetic batches."""
     import torch
-    from oracle import bilinear_oracle as bo
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    from bilinear_b200.model import bilinear as mb
+    import torch.nn as nn
+    torch.manual_seed(seed)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        net, _, _, _ = mb.load(torch.device("cpu"))
-    st = bo.State(net.state_dict(), dtype=torch.float32)
-    x, y, masks = bo.synthetic_batch(1, batch)
-    for _ in range(2):
-        bo.train_step(st, x, y, masks, lr_for(1))
+        bilinear, optimizer, step, _ = ref.load(device)          # model/bilinear.py:58-92
+    criterion = nn.MSELoss()
+    bilinear.train()
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    x = torch.randn(batch, 32, generator=g).to(device)
+    y = torch.randn(batch, 48, generator=g).to(device)
+    for param_group in optimizer.param_groups:                   # train_bilinear.py:66-70 at step == 1
+        param_group['lr'] = lr_for(1)
+
+    def one():
+        optimizer.zero_grad()
+        if autocast:
+            with torch.autocast(device.type, dtype=torch.bfloat16):
+                prediction = bilinear(x)
+            loss = criterion(prediction.float(), y)
+        else:
+            prediction = bilinear(x)
+            loss = criterion(prediction, y)
+        loss.backward()
+        nn.utils.clip_grad_norm_(bilinear.parameters(), max_norm=1)
+        optimizer.step()
+        return loss
+    return one, bilinear, optimizer, (x, y)
+
+
+def cpu_reference_sample(batch_rows, steps, warmup, threads=None):
+    """Time the reference's CPU path on `batch_rows` rows per step.  Returns (poses/s, ms_per_step, threads, kind)."""
+    import torch
+    threads = threads or (os.cpu_count() or 1)
+    torch.set_num_threads(threads)
+    import baseline
+    if baseline.available():
+        one, _, _, _ = reference_step_fn(reference_module(), torch.device("cpu"), batch_rows)
+        kind = "reference"
+    else:       # the staged copy is missing (build() did not run in the build container): fall back to the oracle port
+        from oracle import bilinear_oracle as bo
+        from bilinear_b200.model import bilinear as mb
+        torch.manual_seed(0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            net, _, _, _ = mb.load(torch.device("cpu"))
+        st = bo.State(net.state_dict(), dtype=torch.float32)
+        x, y, masks = bo.synthetic_batch(1, batch_rows)
+        one = lambda: bo.train_step(st, x, y, masks, lr_for(1))
+        kind = "port"
+    for _ in range(max(1, warmup)):
+        one()
     t0 = time.perf_counter()
-    n = 0
-    while n < min_steps or (time.perf_counter() - t0) < seconds_budget:
-        bo.train_step(st, x, y, masks, lr_for(1))
-        n += 1
-        if n >= 2000:
-            break
+    for _ in range(steps):
+        one()
     dt = time.perf_counter() - t0
-    return batch * n / dt, n, threads, dt
+    return batch_rows * steps / dt, dt / steps * 1e3, threads, kind
+
+
+def cpu_baseline_entry(batch):
+    rows = min(batch, CPU_SAMPLE_ROWS)
+    steps = 200 if rows <= 256 else 6
+    v, ms, threads, kind = cpu_reference_sample(rows, steps, 2 if rows > 256 else 20)
+    what = ("unmodified reference module (baseline/_ref/model/bilinear.py) + literal train_bilinear.py:75-83, fp32, torch CPU"
+            if kind == "reference" else "oracle/bilinear_oracle.py port, fp32, torch CPU")
+    return {"value": v, "unit": "poses/s", "cores": threads, "kind": kind,
+            "sample": "%d train iterations of %d rows%s (%.0f ms each): %s"
+                      % (steps, rows, "" if rows == batch else " -- a bounded slice of the %d-row step" % batch, ms, what)}
+
+
+def torch_gpu_arm(device, steps, warmup, configs=(("fp32", 64), ("bf16_autocast", LARGE_BATCH))):
+    """The reference's OWN GPU path: the unmodified module on `device` under torch (util/config.py:17 picks cuda
+    when it is there), eager as written and -- a stronger baseline than the reference itself -- the same
+    iteration captured whole in a CUDA graph.  fp32 at batch 64; at batch 65 536 additionally bf16 autocast."""
+    import torch
+    from bilinear_b200 import parallel
+    ref = reference_module()
+    out = {}
+    for mode, batch in configs:
+        one, net, opt, _ = reference_step_fn(ref, device, batch, autocast=(mode == "bf16_autocast"))
+        small = batch <= 4096
+        k = steps if small else min(steps, 10)
+        for _ in range(max(3, warmup if small else 3)):
+            one()
+        flusher = L2Flusher(device) if small else None
+        if small:
+            ms_eager = timed_steps(torch, parallel, one, k, flusher, device) / k
+        else:
+            ms_eager = timed_block(torch, parallel, one, k, device) / k
+        entry = {"batch": batch, "eager_ms_per_step": ms_eager, "eager_poses_per_s": batch / (ms_eager * 1e-3)}
+        try:
+            # whole-iteration capture (torch "whole network" recipe): capturable Adam, grads set to None inside the graph
+            for grp in opt.param_groups:
+                grp["capturable"] = True
+            for st in opt.state.values():
+                if "step" in st and not st["step"].is_cuda:
+                    st["step"] = st["step"].to(device)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    one()
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                one()
+            for _ in range(3):
+                graph.replay()
+            if small:
+                ms_graph = timed_steps(torch, parallel, graph.replay, k, flusher, device) / k
+            else:
+                ms_graph = timed_block(torch, parallel, graph.replay, k, device) / k
+            entry.update(graph_ms_per_step=ms_graph, graph_poses_per_s=batch / (ms_graph * 1e-3))
+            del graph
+        except Exception as e:      # capture is an extra; the eager number stands on its own
+            entry["graph_error"] = repr(e)[:200]
+        out["train_b%d_%s" % (batch, mode)] = entry
+        del one, net, opt
+        torch.cuda.empty_cache()
+    out["what"] = ("unmodified reference module (baseline/_ref/model/bilinear.py) + literal train_bilinear.py:75-83 on the "
+                   "same B200 under torch %s; same CUDA-event protocol as the headline" % torch.__version__)
+    return out
 
 
 METRIC = "train poses/sec, bilinear MLP (full train_bilinear.py iteration: fwd+MSE+bwd+clip+Adam)"
 
 
 def workload_config(workload, batch, world, fused_dp=True):
-    """`config` of the JSON line -- shared by the B200 arm and the reference (CPU) arm."""
+    """`config` of the JSON line -- identical for the B200 arm and the reference arms."""
     if world > 1:
         par = ("dp%d (local BatchNorm, gradient all-reduce inside the persistent kernel over NVLink peer memory)"
                if fused_dp else "dp%d (local BatchNorm, NCCL all-reduce of the flat gradient)") % world
@@ -382,58 +540,68 @@ def workload_config(workload, batch, world, fused_dp=True):
     return {"workload": "%s: batch %d per GPU, 16 joints, 1024 hidden, 2 residual blocks, random init, "
                         "Philox dropout, clip_grad_norm 1, Adam" % (workload, batch),
             "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": par,
-            "l2": "flushed (256 MB fill) between timed iterations" if batch <= 4096 else "activations exceed L2"}
+            "l2": "flushed (256 MB fill) between timed iterations" if batch <= 4096
+                  else "no flush needed: one step streams > 8 GB of activations through the 126 MB L2"}
+
+
+def batch_of(workload):
+    return 64 if workload == "train_b64" else LARGE_BATCH
 
 
 def run_reference(args, emit):
-    """--impl reference: the CPU arm alone, same metric / config / unit as the GPU arm."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, same metric /
+    config / unit as the B200 arm.  Each step is a bounded sample of the workload: CPU_SAMPLE_ROWS rows of the
+    65 536-row batch (the whole batch at batch 64).  Rank 0 alone runs; the other ranks exit."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    import torch
-    from oracle import bilinear_oracle as bo
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    batch = 64 if args.workload == "train_b64" else 65536
-    if batch > 4096:
-        batch_sample = 4096       # bounded sample of the large-batch step
-    else:
-        batch_sample = batch
-    from bilinear_b200.model import bilinear as mb
-    torch.manual_seed(0)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        net, _, _, _ = mb.load(torch.device("cpu"))
-    st = bo.State(net.state_dict(), dtype=torch.float32)
-    x, y, masks = bo.synthetic_batch(1, batch_sample)
-    for _ in range(max(args.warmup, 1) if batch_sample <= 256 else 1):
-        bo.train_step(st, x, y, masks, lr_for(1))
-    steps = args.steps if batch_sample <= 256 else min(args.steps, 5)
-    steps = min(steps, 2000)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        bo.train_step(st, x, y, masks, lr_for(1))
-    dt = time.perf_counter() - t0
-    value = batch_sample * steps / dt
-    cfg = workload_config(args.workload, batch, max(args.gpus, 1))
-    cfg["reference_arm"] = ("oracle/bilinear_oracle.py (CPU restatement of the reference's PyTorch path; the reference "
-                            "itself is a Python package and does not travel to the GPU box), batch %d per step on %d "
-                            "host threads, rank 0 only" % (batch_sample, threads))
-    line = {
+    batch = batch_of(args.workload)
+    rows = min(batch, CPU_SAMPLE_ROWS)
+    steps = max(1, min(args.steps, 2000 if rows <= 256 else 40))
+    value, ms, threads, kind = cpu_reference_sample(rows, steps, max(1, min(args.warmup, 20 if rows <= 256 else 3)))
+    sample = ("%d iterations of %d rows%s on %d host threads; %s" %
+              (steps, rows, "" if rows == batch else " (bounded slice of the %d-row step)" % batch, threads,
+               "unmodified reference module from baseline/_ref + literal train_bilinear.py:75-83, fp32"
+               if kind == "reference" else "oracle/bilinear_oracle.py port (baseline/_ref not staged), fp32"))
+    emit({
         "impl": "reference", "metric": METRIC,
         "value": value, "unit": "poses/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": cfg,
-        "cpu_baseline": {"value": value, "unit": "poses/s", "cores": threads, "kind": "port",
-                         "sample": "%d iterations of batch %d (oracle/bilinear_oracle.py, float32, torch CPU ops)"
-                                   % (steps, batch_sample)},
+        "config": workload_config(args.workload, batch, max(args.gpus, 1)),
+        "cpu_baseline": {"value": value, "unit": "poses/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    emit(line)
+    })
+
+
+def run_torch_gpu(args, emit):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from bilinear_b200 import parallel  # noqa: F401  (single process: barrier() is a no-op)
+    device = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    batch = batch_of(args.workload)
+    res = torch_gpu_arm(device, max(args.steps, 1), max(args.warmup, 3))
+    key = "train_b%d_%s" % (batch, "fp32" if batch == 64 else "bf16_autocast")
+    best = res[key].get("graph_poses_per_s") or res[key]["eager_poses_per_s"]
+    emit({"impl": "torch_gpu", "metric": METRIC, "value": best, "unit": "poses/s", "n_gpus": 1, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": batch / best * 1e3, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32" if batch == 64 else "bf16 (torch.autocast)", "data": "synthetic",
+          "config": workload_config(args.workload, batch, 1), "torch_gpu": res})
 
 
 # ------------------------------------------------------------------------------------------------ main
+def compact(r, keys=("workload", "value", "unit", "ms_per_step", "ms_per_step_warm_l2", "ms", "launches")):
+    """One flat dict per secondary workload (the driver keeps only the tail of a long line)."""
+    out = {k: r[k] for k in keys if k in r}
+    if "roofline" in r:
+        rf = r["roofline"]
+        out["roofline"] = {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "frac_of_sustained", "note") if k in rf}
+    if "e2e" in r:
+        out["e2e_value"] = r["e2e"]["value"]
+    return out
+
+
 def main():
     # the contract is ONE JSON line on stdout: anything libraries write to file descriptor 1 (e.g. NCCL's
     # version banner) is sent to stderr instead, and the line goes to the saved descriptor at the end
@@ -446,16 +614,32 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="train_b64", choices=["train_b64", "train_b65536"])
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_gpu"])
+    ap.add_argument("--workload", default="train_b65536", choices=["train_b65536", "train_b64"])
     ap.add_argument("--no-also", action="store_true", help="skip the secondary BASELINE configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    ap.add_argument("--no-torch", action="store_true", help="skip the torch-on-B200 baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args, emit)
         return
+    if args.impl == "torch_gpu":
+        run_torch_gpu(args, emit)
+        return
+
+    rank0 = int(os.environ.get("RANK", "0")) == 0
+    batch = batch_of(args.workload)
+    # The CPU baseline is taken on rank 0 BEFORE the process group exists: torchrun exports OMP_NUM_THREADS=1 and,
+    # once NCCL is up, the other ranks spin in the barrier on the cores the CPU arm needs (round 1 reported a
+    # 200x too low figure at N > 1 for exactly that reason).  The other ranks wait in the rendezvous meanwhile.
+    cpu = None
+    if rank0 and not args.no_cpu:
+        try:
+            cpu = cpu_baseline_entry(batch)
+        except Exception as e:
+            cpu = {"value": None, "unit": "poses/s", "cores": 0, "kind": "port", "sample": "failed: " + repr(e)[:200]}
 
     import torch
     from bilinear_b200 import _lib, parallel
@@ -474,38 +658,51 @@ def main():
     if sampler:
         sampler.start()
     if args.workload == "train_b64":
-        main_res = bench_train(args, "fp32", 64, steps, warmup, device, world, peaks)
-        dtype, batch = "f32 (3 x bf16 split operands on tcgen05, fp32 accumulate)", 64
+        main_res = bench_train("fp32", 64, steps, warmup, device, world, peaks)
+        dtype = "f32 (3 x bf16 split operands on tcgen05, fp32 accumulate)"
     else:
-        main_res = bench_train(args, "bf16", 65536, min(steps, 20), warmup, device, world, peaks, flush=False)
-        dtype, batch = "bf16", 65536
-        steps = min(steps, 20)
+        main_res = bench_train("bf16", LARGE_BATCH, steps, warmup, device, world, peaks)
+        dtype = "bf16"
     clocks = sampler.stop() if sampler else None
 
     also = []
     if not args.no_also:
-        s2 = 10
-        try:
-            if args.workload != "train_b65536":
-                r = bench_train(args, "bf16", 65536, s2, 3, device, world, peaks, flush=False, with_e2e=True)
-                r["workload"] = "train_b65536_bf16"; r["unit"] = "poses/s"
-                r["l2"] = "activations (>1 GB per step) exceed L2"
-                also.append(r)
-            r = bench_train(args, "bf16", 64, steps, warmup, device, world, peaks, with_e2e=False)
-            r["workload"] = "train_b64_bf16"; r["unit"] = "poses/s"; r["l2"] = "flushed between iterations"
-            also.append(r)
-            also.append(bench_infer(10_000_000, 65536, "bf16", 3, 1, device, rank, world, peaks))
-            also.append(bench_infer(10_000_000, 65536, "fp32", 2, 1, device, rank, world, peaks))
-            also.append(bench_eval(1_000_000, 50, 5, device, rank, world, peaks))
-        except Exception as e:  # a secondary config must not take the headline down with it
-            also.append({"error": repr(e)[:400]})
+        def guarded(fn):
+            try:
+                also.append(fn())
+            except Exception as e:  # a secondary config must not take the headline down with it
+                also.append({"error": repr(e)[:300]})
+        if args.workload == "train_b65536":
+            def small():
+                r = bench_train("fp32", 64, max(steps, 100), warmup, device, world, peaks)
+                r["workload"] = "train_b64_fp32 per GPU (BASELINE configs[1]: persistent whole-network kernel; L2 flushed)"
+                r["unit"] = "poses/s"
+                return compact(r)
+            guarded(small)
+            if world > 1:
+                def strong():
+                    r = bench_train("bf16", LARGE_BATCH // world, steps, warmup, device, world, peaks, with_e2e=False)
+                    r["workload"] = "train_b65536_GLOBAL_bf16 (strong scaling: %d rows per GPU)" % (LARGE_BATCH // world)
+                    r["unit"] = "poses/s"
+                    return compact(r)
+                guarded(strong)
+        else:
+            def large():
+                r = bench_train("bf16", LARGE_BATCH, min(steps, 20), 3, device, world, peaks)
+                r["workload"] = "train_b65536_bf16 per GPU"
+                r["unit"] = "poses/s"
+                return compact(r)
+            guarded(large)
+        guarded(lambda: compact(bench_infer(10_000_000, 65536, "bf16", 3, 1, device, rank, world, peaks)))
+        guarded(lambda: compact(bench_infer(10_000_000, 65536, "fp32", 2, 1, device, rank, world, peaks)))
+        guarded(lambda: bench_eval(1_000_000, 50, 5, device, rank, world, peaks))
 
-    cpu = None
-    if rank == 0 and not args.no_cpu:
-        v, n, threads, dt = cpu_train_sample(64, 12.0)
-        cpu = {"value": v, "unit": "poses/s", "cores": threads, "kind": "port",
-               "sample": "%d train iterations of batch 64 in %.1f s (oracle/bilinear_oracle.py, float32, torch CPU ops)"
-                         % (n, dt)}
+    torch_gpu = None
+    if rank == 0 and not args.no_torch:
+        try:
+            torch_gpu = torch_gpu_arm(device, max(steps, 50), warmup)
+        except Exception as e:
+            torch_gpu = {"error": repr(e)[:300]}
     parallel.barrier()
 
     if rank == 0:
@@ -517,9 +714,10 @@ def main():
             "config": workload_config(args.workload, batch, world, os.environ.get("BILINEAR_B200_DP", "fused") == "fused"),
             "roofline": main_res["roofline"], "e2e": main_res.get("e2e"),
             "gpu_launches": main_res["launches"], "clocks": clocks, "cpu_baseline": cpu,
-            "ms_per_step_warm_l2": main_res.get("ms_per_step_warm_l2"),
-            "also": also,
+            "torch_gpu": torch_gpu, "also": also,
         }
+        if "ms_per_step_warm_l2" in main_res:
+            line["ms_per_step_warm_l2"] = main_res["ms_per_step_warm_l2"]
         emit(line)
     if world > 1:
         import torch.distributed as dist

@@ -86,6 +86,16 @@ struct Dyn {
 
 enum DynSrc : int32_t { SRC_NONE = 0, SRC_X = 1, SRC_DP = 2 };
 
+// Chunk gating between an apply pass and the GEMM tiles of the same phase (helper-warp build).
+constexpr int kGateShift = 11;
+constexpr int kGateCols = 1 << kGateShift;   // 2048 batch columns = 32 k-blocks = one wgrad K slice
+enum GateKind : int32_t {
+  GATE_NONE = 0,
+  GATE_N = 1,   // the tile's n range is a batch range (forward / dgrad GEMMs: activations are the B operand)
+  GATE_K = 2,   // the tile's k range is a batch range (wgrad: dz is the K-major A operand)
+  GATE_M = 3,   // the tile's m range is a batch range (transposed decode: activations are the A operand)
+};
+
 constexpr int kMaxZero = 8;
 
 // BatchNorm folding table for eval mode (one per plan, in device memory; EW_BN_FOLD via Args::fold).
@@ -190,6 +200,11 @@ struct alignas(16) Args {
   const CommTab* comm;     // EW_COMM_BARRIER / EW_ALLREDUCE; EW_ADAM: clip norm from the exchanged slice sums
   int32_t comm_step;       // EW_COMM_BARRIER: 0 = before the exchange, 1 = after it (publishes the slice sum)
   int32_t pad_c;
+  // ---- overlap of the large-batch BatchNorm apply passes with the GEMM that consumes their output (helper-warp
+  // build, mega_pairx.cu): the apply pass walks the batch in chunks of kGateCols columns, all 1024 features of a
+  // chunk before the next chunk, and counts finished (feature, chunk) items in gate[chunk]; GEMM tiles whose
+  // operand lies in that chunk start once the counter reaches kHidden (GemmJob::gate)
+  uint32_t* gate;          // EW_BN_FWD_APPLY / EW_BN_BWD_APPLY: per-chunk arrival counters (nullptr: no consumer waits)
 };
 
 struct alignas(16) GemmJob {
@@ -201,7 +216,9 @@ struct alignas(16) GemmJob {
   int32_t ksplit;          // >= 1: number of K slices (tile index = (ks * n_tiles + nt) * m_tiles + mt)
   int32_t kb_per_split;    // 64-element k-blocks per slice
   int32_t epi;
-  int32_t pad_[3];
+  int32_t gate_kind;       // GateKind: which extent of the tile lies along the batch (the gated dimension)
+  int32_t pad_[2];
+  const uint32_t* gate;    // per-chunk counters written by the apply pass running in the same phase (nullptr: none)
   Args a;
 };
 
@@ -220,6 +237,8 @@ struct Phase {
                                   // tile-id lists (CtaTiles::begin/end index into it)
   int32_t pf_slice, pf_slices;    // pf_slices > 0: during this phase an idle warp prefetches slice pf_slice of
                                   // pf_slices of the optimizer's p / m / v arrays into L2 (MegaParams::adam)
+  int32_t ew_first;               // helper-warp build: the elementwise jobs run CONCURRENTLY with the GEMM tiles of
+  int32_t pad_p;                  // the phase (on their own warps); elsewhere they run after the CTA's tiles
 };
 
 // Everything a CTA needs to know about one phase, contiguous in device memory.  All 256 threads copy
