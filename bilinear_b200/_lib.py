@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbilinear_b200.so")
+# BILINEAR_B200_LIB: an alternative build of the same library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("BILINEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbilinear_b200.so")
 
 PARAM_NUMEL = 4291632
 NUM_BN = 5

@@ -20,8 +20,9 @@
 #include "jobs.h"
 
 namespace b200 {
-cudaError_t launch_mega(const MegaParams& p, int grid, bool cooperative, cudaStream_t stream, int cg);
+cudaError_t launch_mega(const MegaParams& p, int grid, bool cooperative, cudaStream_t stream, int variant);
 int mega_pair_max_clusters(int grid);
+int mega_pairx_max_clusters(int grid);
 int mega_ring_bytes();
 struct EvalParams {
   const float* pred; const float* gt; const float* mean; const float* stddev; const int32_t* action;
@@ -145,6 +146,8 @@ struct Bufs {
   float* x_save;                     // small path: copy of the input batch [Bs][32] fp32
   float* x_stage; float* y_stage; float* p_stage; float* scalars;   // device ends of the *_host entry points
   uint8_t* acc_base; int64_t acc_bytes;
+  uint32_t* gates_f[kNumHeavy]; uint32_t* gates_b[kNumHeavy];   // helper-warp build: per-chunk counters of the apply passes
+  int64_t gate_words;
   double* loss_acc; double* gnorm2; double* stats_f[kNumHeavy]; double* stats_b[kNumHeavy];
   float* save_mean[kNumHeavy]; float* save_rstd[kNumHeavy]; float* scale[kNumHeavy]; float* shift[kNumHeavy];
   PlaneRef W[kNumLinear];
@@ -193,6 +196,11 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
   u.gnorm2 = u.loss_acc ? u.loss_acc + 8 : nullptr;
   for (int l = 0; l < kNumHeavy; ++l) u.stats_f[l] = c.take_n<double>(2 * kHidden);
   for (int l = 0; l < kNumHeavy; ++l) u.stats_b[l] = c.take_n<double>(2 * kHidden);
+  // chunk gates (helper-warp build): one counter per 2048 batch columns, per layer and direction; cleared with
+  // the accumulators at the start of every step
+  u.gate_words = ((Bs + kGateCols - 1) / kGateCols + 63) & ~int64_t(63);
+  for (int l = 0; l < kNumHeavy; ++l) u.gates_f[l] = c.take_n<uint32_t>(u.gate_words);
+  for (int l = 0; l < kNumHeavy; ++l) u.gates_b[l] = c.take_n<uint32_t>(u.gate_words);
   c.take(0);
   u.acc_base = c.base ? c.base + acc0 : nullptr;
   u.acc_bytes = ((c.off + 1023) & ~int64_t(1023)) - acc0;
@@ -250,6 +258,8 @@ struct b200_plan {
   bool large;
   int sms;
   int cg = 1;                // CTAs per MMA: 2 = CTA pairs (large-batch plans), 1 otherwise
+  bool helpers = false;      // CTA pairs + helper warps: apply passes overlap the GEMM that consumes them (mega_pairx.cu)
+  int variant() const { return helpers ? 3 : cg; }
   int workers() const { return sms / cg; }
   std::vector<CUtensorMap> tm;
   std::vector<PhaseBlob> blobs;
@@ -274,6 +284,7 @@ static int add_map(b200_plan* pl, const PlaneRef& r, int64_t inner, int64_t rows
 
 static void begin_phase(b200_plan* pl) {
   memset(&pl->cur, 0, sizeof pl->cur);
+  pl->cur.ph.aux_off = -1;
   pl->cur.ph.stage_bytes = 1024;
   pl->cur.ph.num_stages = 1;
   pl->cur.ph.sched_off = -1;
@@ -289,6 +300,12 @@ static int end_phase(b200_plan* pl) {
   }
   p.stage_bytes = sb;
   p.num_stages = std::max(1, std::min(8, mega_ring_bytes() / sb));
+  p.aux_off = -1;
+  if (pl->helpers && p.num_ew > 0) {
+    // the apply pass keeps its per-feature constants in the part of the ring region the operand stages leave free
+    if (mega_ring_bytes() - p.num_stages * sb < kAuxBytes && p.num_stages > 3) --p.num_stages;
+    if (mega_ring_bytes() - p.num_stages * sb >= kAuxBytes) p.aux_off = p.num_stages * sb;
+  }
   const int G = pl->workers();   // CTAs, or CTA pairs walking one tile list
   std::vector<CtaTiles> ct(G);
   for (int c = 0; c < G; ++c) memset(&ct[c], 0, sizeof(CtaTiles));
@@ -313,7 +330,33 @@ static int end_phase(b200_plan* pl) {
         tiles.push_back(T{id, int64_t(kb) * pairs * g.BN + epi});
       }
     }
-    std::stable_sort(tiles.begin(), tiles.end(), [](const T& a, const T& b) { return a.cost > b.cost; });
+    bool gated = false;
+    for (int j = 0; j < p.num_gemm; ++j) gated = gated || pl->cur.gj[j].gate != nullptr;
+    if (gated) {
+      // Tiles that wait for a chunk of the apply pass running in this phase: every CTA walks its list in CHUNK
+      // order (the pass finishes chunk c before chunk c + 1), heavier tiles first within a chunk; tiles go to
+      // the least-loaded CTA in that order, which balances the phase to within one tile.
+      std::vector<int> chunk(tiles.size());
+      int id2 = 0;
+      for (int j = 0; j < p.num_gemm; ++j) {
+        const GemmJob& g = pl->cur.gj[j];
+        for (int t = 0; t < g.num_tiles; ++t, ++id2) {
+          const int mt = t % g.m_tiles, nt = (t / g.m_tiles) % g.n_tiles, ks = t / (g.m_tiles * g.n_tiles);
+          int hi = 0;
+          if (g.gate == nullptr) hi = 0;
+          else if (g.gate_kind == GATE_N) hi = std::min(g.N, (nt + 1) * g.BN) - 1;
+          else if (g.gate_kind == GATE_K) hi = std::min(g.K, (ks + 1) * g.kb_per_split * 64) - 1;
+          else hi = std::min(g.M, (mt + 1) * 128 * pl->cg) - 1;
+          chunk[id2] = g.gate ? (hi >> kGateShift) : -1;   // ungated tiles of the phase can start at once
+        }
+      }
+      std::stable_sort(tiles.begin(), tiles.end(), [&](const T& a, const T& b) {
+        if (chunk[a.id] != chunk[b.id]) return chunk[a.id] < chunk[b.id];
+        return a.cost > b.cost;
+      });
+    } else {
+      std::stable_sort(tiles.begin(), tiles.end(), [](const T& a, const T& b) { return a.cost > b.cost; });
+    }
     std::vector<std::vector<int>> per(G);
     typedef std::pair<int64_t, int> LoadCta;
     std::priority_queue<LoadCta, std::vector<LoadCta>, std::greater<LoadCta>> pq;
@@ -355,7 +398,7 @@ static Args base_args(const b200_plan* pl, int layer) {
 // D[m][n] = sum_k A[m][k] B[n][k].  K-major operand: global [rows = m|n][inner = k];
 // MN-major operand (x_mn = 1): global [rows = k][inner = m|n] -- the feature-major activations.
 static int add_gemm(b200_plan* pl, const PlaneRef& A, int a_mn, const PlaneRef& Bop, int b_mn, int M, int N, int K,
-                    int BN, int epi, const Args& a, int ksplit = 1) {
+                    int BN, int epi, const Args& a, int ksplit = 1, int gate_kind = GATE_NONE, const uint32_t* gate = nullptr) {
   if (pl->cur.ph.num_gemm >= kBlobGemm) return fail("too many gemm jobs in one phase");
   if (b_mn && BN % 64) return fail("MN-major B operand needs a tile width that is a multiple of 64");
   GemmJob g;
@@ -375,6 +418,8 @@ static int add_gemm(b200_plan* pl, const PlaneRef& A, int a_mn, const PlaneRef& 
   g.ksplit = (num_kb + g.kb_per_split - 1) / g.kb_per_split;   // no empty slices
   g.num_tiles = g.m_tiles * g.n_tiles * g.ksplit;
   g.epi = epi;
+  g.gate_kind = gate ? gate_kind : GATE_NONE;
+  g.gate = gate;
   g.a = a;
   pl->cur.gj[pl->cur.ph.num_gemm++] = g;
   return 0;
@@ -439,11 +484,10 @@ static void small_part_args(const b200_plan* pl, Args& a) {
   a.part_stride = int64_t(kHidden) * pl->u.Bs;
 }
 
-// forward heavy layer l (model/bilinear.py:7-13) -- train or eval flavour
-static int build_fwd_layer(b200_plan* pl, int l, bool train, bool phase_open = false) {
+// Args of forward heavy layer l (model/bilinear.py:7-13): shared by its GEMM epilogue and its apply pass
+static Args fwd_layer_args(const b200_plan* pl, int l, bool train) {
   const Bufs& u = pl->u;
   const b200_plan_desc& d = pl->d;
-  const int B = pl->B;
   Args a = base_args(pl, l);
   a.bias = d.params + kPL.b[l];
   a.gamma = d.params + kPL.g[l];
@@ -459,9 +503,34 @@ static int build_fwd_layer(b200_plan* pl, int l, bool train, bool phase_open = f
   if (l == 4) a.skip_fm = u.h_fm[2];
   a.out_fm = u.h_fm[l];
   a.eval_mode = train ? 0 : 1;
+  return a;
+}
+
+// forward heavy layer l (model/bilinear.py:7-13) -- train or eval flavour
+static int build_fwd_layer(b200_plan* pl, int l, bool train, bool phase_open = false) {
+  const Bufs& u = pl->u;
+  const b200_plan_desc& d = pl->d;
+  const int B = pl->B;
+  Args a = fwd_layer_args(pl, l, train);
   const PlaneRef& in = (l == 0) ? u.X_fm : u.h_fm[l - 1];
   const int K = kPL.cols[l];
   const int BN = tile_bn(pl, B);
+  if (pl->helpers && train) {
+    // Helper-warp build: ONE phase per layer.  The apply pass of the PREVIOUS layer (z -> BatchNorm -> ReLU ->
+    // dropout (+ skip) -> h, needs that layer's complete batch statistics, hence the grid barrier in front) runs
+    // on the helper warps chunk by chunk while the GEMM roles multiply the chunks that are through.
+    begin_phase(pl);
+    pl->cur.ph.ew_first = 1;
+    const uint32_t* gate = nullptr;
+    if (l > 0) {
+      Args pa = fwd_layer_args(pl, l - 1, true);
+      pa.gate = u.gates_f[l - 1];
+      gate = pa.gate;
+      if (add_ew(pl, EW_BN_FWD_APPLY, pa)) return 1;
+    }
+    if (add_gemm(pl, u.W[l], 0, in, 1, kHidden, B, K, BN, EPI_FWD_LARGE, a, 1, GATE_N, gate)) return 1;
+    return end_phase(pl);
+  }
   if (!pl->large) {
     small_part_args(pl, a);
     a.drop = nullptr;   // dropout bits are drawn inline (drop_word)
@@ -520,13 +589,22 @@ static int build_decode(b200_plan* pl, bool fuse_loss, bool train) {
     return 0;
   }
   begin_phase(pl);
+  const uint32_t* gate = nullptr;
+  if (pl->helpers && train) {
+    // helper-warp build: the apply pass of the last heavy layer shares the phase with the decode GEMM
+    pl->cur.ph.ew_first = 1;
+    Args pa = fwd_layer_args(pl, kNumHeavy - 1, true);
+    pa.gate = u.gates_f[kNumHeavy - 1];
+    gate = pa.gate;
+    if (add_ew(pl, EW_BN_FWD_APPLY, pa)) return 1;
+  }
   {
     // Large batches: the decode GEMM runs TRANSPOSED -- P[b][48] = h[b][:] . W5^T with the activations as an
     // MN-major A operand (128 poses per tile) and the 48 x 1024 weight as the K-major B operand.  With rows =
     // output features only 48 of the 128 accumulator lanes (1.5 of the 4 epilogue warps) carry data and every
     // prediction / target access is a 4-byte access at a 192-byte stride; with rows = poses each lane owns
     // one pose: 192 contiguous bytes of target in, 192 contiguous bytes of prediction out.
-    if (add_gemm(pl, u.h_fm[4], 1, u.W[5], 0, pl->B, kDout, kHidden, kDout, EPI_DECODE_T, a)) return 1;
+    if (add_gemm(pl, u.h_fm[4], 1, u.W[5], 0, pl->B, kDout, kHidden, kDout, EPI_DECODE_T, a, 1, GATE_M, gate)) return 1;
   }
   if (end_phase(pl)) return 1;
   return 0;
@@ -552,7 +630,7 @@ static int build_backward(b200_plan* pl, bool with_norm, const Args* tail_ew, in
   const int B = pl->B;
   const int wsplit = wgrad_split(pl);
   double* wnorm = (with_norm && wsplit == 1) ? u.gnorm2 : nullptr;   // split-K: EW_SUMSQ over everything instead
-  for (int l = 4; l >= 0; --l) {
+  auto layer_args = [&](int l) {
     Args a = base_args(pl, l);
     a.gamma = d.params + kPL.g[l];
     a.save_mean = u.save_mean[l]; a.save_rstd = u.save_rstd[l];
@@ -565,6 +643,43 @@ static int build_backward(b200_plan* pl, bool with_norm, const Args* tail_ew, in
     a.grad_bias = d.grads + kPL.b[l];
     a.grad_gamma = d.grads + kPL.g[l];
     a.grad_beta = d.grads + kPL.be[l];
+    return a;
+  };
+  if (pl->helpers) {
+    // Helper-warp build: the apply pass of layer l + 1 (dy, z -> dz; needs the complete sums of dy and dy * xhat)
+    // shares a phase with the two GEMMs that consume dz_{l+1}: the dgrad towards layer l (dz is its B operand:
+    // tiles gated by batch columns) and the wgrad of Linear l + 1 (dz is its K-major A operand: K slices gated).
+    for (int l = 4; l >= -1; --l) {
+      const int up = l + 1;
+      begin_phase(pl);
+      pl->cur.ph.ew_first = 1;
+      const uint32_t* gate = nullptr;
+      if (up <= 4) {
+        Args pa = layer_args(up);
+        pa.gate = u.gates_b[up];
+        gate = pa.gate;
+        if (add_ew(pl, EW_BN_BWD_APPLY, pa)) return 1;
+      }
+      const PlaneRef& dzu = (up == 5) ? u.dP_fm : u.dz_fm[up];
+      if (l >= 0) {
+        Args a = layer_args(l);
+        if (add_gemm(pl, u.W[up], 1, dzu, 1, kHidden, B, kPL.rows[up], tile_bn(pl, B), EPI_DGRAD_LARGE, a, 1, GATE_N, gate))
+          return 1;
+      }
+      Args w = base_args(pl, up);
+      w.out_f32 = d.grads + kPL.w[up];
+      w.ld_out = kPL.cols[up];
+      w.gnorm2 = wnorm;
+      const PlaneRef& hin = (l >= 0) ? u.h_fm[l] : u.X_fm;
+      const int BNw = (l >= 0) ? tile_bn_feat(pl, kHidden) : 32;
+      if (add_gemm(pl, dzu, 0, hin, 0, kPL.rows[up], kPL.cols[up], B, BNw, EPI_WGRAD, w, wsplit, GATE_K, gate)) return 1;
+      if (end_phase(pl)) return 1;
+    }
+    (void)tail_ew; (void)tail_kind;
+    return 0;
+  }
+  for (int l = 4; l >= 0; --l) {
+    Args a = layer_args(l);
     const int up = l + 1;                      // the Linear whose input is h_l
     const int Kd = kPL.rows[up];               // 1024, or 48 for decode
     const PlaneRef& dzu = (up == 5) ? u.dP_fm : u.dz_fm[up];
@@ -693,6 +808,9 @@ static int build_plan(b200_plan* pl) {
     Args a = base_args(pl, 5);
     int k = 0;
     for (int l = 0; l < kNumHeavy; ++l) { a.zero_ptr[k] = u.stats_b[l]; a.zero_bytes[k] = 2 * kHidden * 8; ++k; }
+    // the chunk gates of the backward apply passes lie contiguously behind each other (carve)
+    a.zero_ptr[k] = u.gates_b[0]; a.zero_bytes[k] = (reinterpret_cast<uint8_t*>(u.gates_b[kNumHeavy - 1]) -
+                                                     reinterpret_cast<uint8_t*>(u.gates_b[0])) + u.gate_words * 4; ++k;
     if (add_ew(pl, EW_PREP, a)) return 1;
     if (pl->large) {
       Args z = base_args(pl, 5);
@@ -717,13 +835,15 @@ static int build_plan(b200_plan* pl) {
     if (build_backward(pl, true, nullptr, 0, true)) return 1;
   } else {
     Args a = adam_args(pl);
-    if (wgrad_split(pl) == 1) {
+    if (wgrad_split(pl) == 1 && !pl->helpers) {
       // the weight tiles were squared in the wgrad epilogues: only bias / BN-affine gradients are left,
       // and those were final before the last GEMM phase started
       a.src_cols = 1;
       if (build_backward(pl, true, &a, EW_SUMSQ)) return 1;
     } else {
-      a.src_cols = 0;
+      // (helper-warp build: the last apply pass shares the last GEMM phase, so the bias / BN-affine gradients are
+      // final only after it -- the sum of squares always gets its own phase)
+      a.src_cols = (wgrad_split(pl) == 1) ? 1 : 0;
       if (build_backward(pl, true, nullptr, 0)) return 1;
       begin_phase(pl);
       if (add_ew(pl, EW_SUMSQ, a)) return 1;
@@ -801,12 +921,17 @@ static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, c
   p.phase_ns = pl->u.phase_ns;
   pl->last_first = s.first; pl->last_count = count;
   p.num_phases = count;
+  static const uint32_t dbg = getenv("B200_DBG") ? uint32_t(atoi(getenv("B200_DBG"))) : 0u;
+  p.dbg = dbg;
   p.dyn = dyn;
-  const bool coop = count > 1;
+  // B200_NOCOOP=1 (profiling only): ncu cannot launch the cooperative cluster kernel (LaunchFailed); the grid is one
+  // CTA per SM, so all CTAs are co-resident in practice and the grid barrier still works (a 2 s timeout traps otherwise)
+  static const bool nocoop = getenv("B200_NOCOOP") && atoi(getenv("B200_NOCOOP")) == 1;
+  const bool coop = count > 1 && !nocoop;
   p.bar_base = pl->bar_count;
   const int grid = pl->workers() * pl->cg;
   pl->bar_count += uint32_t(grid) * uint32_t(count - 1);
-  CK(launch_mega(p, grid, coop, stream, pl->cg));
+  CK(launch_mega(p, grid, coop, stream, pl->variant()));
   g_launches.fetch_add(1);
   return 0;
 }
@@ -832,6 +957,20 @@ static Dyn make_dyn(const b200_train_args* t, const b200_adam_args* a) {
     d.grad_scale = a->grad_scale;
   }
   return d;
+}
+
+__global__ void unblock_keep_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int ldw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kHidden * ldw) return;
+  const int f = i / ldw, w = i - f * ldw;
+#ifndef B200_BLOCKED
+#define B200_BLOCKED 0
+#endif
+#if B200_BLOCKED
+  dst[i] = src[((int64_t(f >> 5) * ldw + w) << 5) + (f & 31)];
+#else
+  dst[i] = src[i];
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -879,6 +1018,10 @@ int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
   cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, dev);
   // pairs need one resident cluster per two SMs under the cooperative launch; otherwise the single-CTA build
   if (pl->cg == 2 && mega_pair_max_clusters(pl->sms) < pl->sms / 2) pl->cg = 1;
+  // B200_HELPERS=1 (experiment, off by default): CTA pairs + helper warps (24 warps per CTA), the BatchNorm apply passes
+  // of a training plan overlap the GEMM that consumes their output (mega_pairx.cu; measured in DESIGN.md section 8).
+  pl->helpers = pl->cg == 2 && getenv("B200_HELPERS") && atoi(getenv("B200_HELPERS")) == 1 &&
+                mega_pairx_max_clusters(pl->sms) >= pl->sms / 2;
   Carver c(desc->workspace);
   carve(c, pl->u, pl->B, pl->P, pl->kind);
   if (build_plan(pl)) { delete pl; return 1; }
@@ -1136,6 +1279,13 @@ int b200_debug_keep_bits(b200_plan* plan, int32_t layer, uint32_t* out, void* st
   if (!plan || !out) return fail("null argument");
   if (layer < 0 || layer >= kNumHeavy) return fail("layer must be in [0, 5)");
   if (plan->kind != B200_PLAN_TRAIN || !plan->u.keep[layer]) return fail("training plan required");
+  if (plan->large) {
+    // large-batch plans keep the words in 32-feature bands (mega.cu: blk_word): hand them out as [1024][ldw]
+    const int total = kHidden * int(plan->u.ldw);
+    unblock_keep_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(plan->u.keep[layer], out, int(plan->u.ldw));
+    CK(cudaGetLastError());
+    return 0;
+  }
   CK(cudaMemcpyAsync(out, plan->u.keep[layer], size_t(kHidden) * plan->u.ldw * 4, cudaMemcpyDeviceToDevice,
                      (cudaStream_t)stream));
   return 0;

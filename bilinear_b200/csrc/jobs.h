@@ -238,8 +238,11 @@ struct Phase {
   int32_t pf_slice, pf_slices;    // pf_slices > 0: during this phase an idle warp prefetches slice pf_slice of
                                   // pf_slices of the optimizer's p / m / v arrays into L2 (MegaParams::adam)
   int32_t ew_first;               // helper-warp build: the elementwise jobs run CONCURRENTLY with the GEMM tiles of
-  int32_t pad_p;                  // the phase (on their own warps); elsewhere they run after the CTA's tiles
+                                  // the phase (on their own warps); elsewhere they run after the CTA's tiles
+  int32_t aux_off;                // helper-warp build: byte offset inside the ring region of >= kAuxBytes that the
+                                  // operand ring of this phase leaves free (per-feature tables of the apply pass); < 0: none
 };
+constexpr int kAuxBytes = 16 * 1024;
 
 // Everything a CTA needs to know about one phase, contiguous in device memory.  All 256 threads copy
 // the NEXT phase's blob into shared memory while thread 0 waits in the grid barrier, so no role ever
@@ -269,6 +272,7 @@ struct MegaParams {
   unsigned int* barrier;    // grid barrier counter: monotonic across launches (never reset), see bar_base
   unsigned long long* phase_ns;  // [8 * (num_phases + 1)] globaltimer stamps written by block 0 (nullptr: off)
   int32_t num_phases;
+  uint32_t dbg;             // timing experiments only (B200_DBG): 1 = skip the GEMM tiles, 2 = skip the apply passes and gates
   uint32_t bar_base;        // value of *barrier when this launch starts (the host keeps count)
   Dyn dyn;
 };
