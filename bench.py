@@ -128,6 +128,12 @@ class ClockSampler:
                 "samples_under_load": len(busy), "reasons": sorted(reasons)}
 
 
+def note(msg):
+    """Progress line on stderr (stdout carries the one JSON line only)."""
+    sys.stderr.write("[bench %s r%s] %s\n" % (time.strftime("%H:%M:%S"), os.environ.get("RANK", "0"), msg))
+    sys.stderr.flush()
+
+
 def make_model(precision, device, seed=0):
     import torch
     from bilinear_b200.model import bilinear as mb
@@ -290,8 +296,10 @@ def bench_train(precision, batch, steps, warmup, device, world, peaks, with_e2e=
     from bilinear_b200 import _lib, parallel
     small = batch <= 4096
     loop = TrainLoop(precision, batch, device, world, nbatches=(64 if small else 3))
+    note("train %s B=%d: warm-up" % (precision, batch))
     for _ in range(max(warmup, 3)):
         loop.one()
+    note("train %s B=%d: timed" % (precision, batch))
     n0 = _lib.lib().b200_launch_count()
     if small:
         flusher = L2Flusher(device)
@@ -305,6 +313,7 @@ def bench_train(precision, batch, steps, warmup, device, world, peaks, with_e2e=
     if small:   # steady state, parameters L2-resident (no flush) -- reported beside the flushed number
         res["ms_per_step_warm_l2"] = timed_steps(torch, parallel, loop.one, steps, None, device) / steps
     if with_e2e:
+        note("train %s B=%d: e2e" % (precision, batch))
         if small and world == 1:
             for _ in range(3):
                 loop.e2e_small()
@@ -461,15 +470,20 @@ def cpu_reference_sample(batch_rows, steps, warmup, threads=None):
     return batch_rows * steps / dt, dt / steps * 1e3, threads, kind
 
 
-def cpu_baseline_entry(batch):
-    rows = min(batch, CPU_SAMPLE_ROWS)
-    steps = 200 if rows <= 256 else 6
-    v, ms, threads, kind = cpu_reference_sample(rows, steps, 2 if rows > 256 else 20)
-    what = ("unmodified reference module (baseline/_ref/model/bilinear.py) + literal train_bilinear.py:75-83, fp32, torch CPU"
-            if kind == "reference" else "oracle/bilinear_oracle.py port, fp32, torch CPU")
-    return {"value": v, "unit": "poses/s", "cores": threads, "kind": kind,
-            "sample": "%d train iterations of %d rows%s (%.0f ms each): %s"
-                      % (steps, rows, "" if rows == batch else " -- a bounded slice of the %d-row step" % batch, ms, what)}
+def cpu_baseline_entry(workload, budget_s=120):
+    """The CPU baseline of the JSON line: `bench.py --impl reference` in a CHILD process with a clean threading
+    environment.  torchrun exports OMP_NUM_THREADS=1 to every rank, and an OpenMP runtime that was initialised with
+    one thread does not grow back reliably -- round 1 reported a 200x too low figure at N > 1 that way."""
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT",
+                        "TORCHELASTIC_RUN_ID", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE")}
+    env["CUDA_VISIBLE_DEVICES"] = ""          # the child is the CPU arm: it must not touch the GPUs
+    small = workload == "train_b64"
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+           "--steps", "200" if small else "6", "--warmup", "20" if small else "2"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=budget_s)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    return line["cpu_baseline"]
 
 
 def torch_gpu_arm(device, steps, warmup, configs=(("fp32", 64), ("bf16_autocast", LARGE_BATCH))):
@@ -637,7 +651,8 @@ def main():
     cpu = None
     if rank0 and not args.no_cpu:
         try:
-            cpu = cpu_baseline_entry(batch)
+            note("cpu baseline")
+            cpu = cpu_baseline_entry(args.workload)
         except Exception as e:
             cpu = {"value": None, "unit": "poses/s", "cores": 0, "kind": "port", "sample": "failed: " + repr(e)[:200]}
 
@@ -646,6 +661,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
     _lib.lib()
+    note("process group")
     rank, local_rank, world = parallel.init()
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("--gpus %d needs torchrun with --nproc-per-node %d" % (args.gpus, args.gpus))
@@ -657,6 +673,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    note("headline %s" % args.workload)
     if args.workload == "train_b64":
         main_res = bench_train("fp32", 64, steps, warmup, device, world, peaks)
         dtype = "f32 (3 x bf16 split operands on tcgen05, fp32 accumulate)"
@@ -668,6 +685,7 @@ def main():
     also = []
     if not args.no_also:
         def guarded(fn):
+            note("also #%d" % len(also))
             try:
                 also.append(fn())
             except Exception as e:  # a secondary config must not take the headline down with it
@@ -698,8 +716,9 @@ def main():
         guarded(lambda: bench_eval(1_000_000, 50, 5, device, rank, world, peaks))
 
     torch_gpu = None
-    if rank == 0 and not args.no_torch:
+    if rank == 0 and world == 1 and not args.no_torch:     # (a single-GPU baseline: measured in the N = 1 run only)
         try:
+            note("torch-on-B200 arm")
             torch_gpu = torch_gpu_arm(device, max(steps, 50), warmup)
         except Exception as e:
             torch_gpu = {"error": repr(e)[:300]}
