@@ -23,6 +23,8 @@ namespace b200 {
 cudaError_t launch_mega(const MegaParams& p, int grid, bool cooperative, cudaStream_t stream, int variant);
 int mega_pair_max_clusters(int grid);
 int mega_pairx_max_clusters(int grid);
+cudaError_t launch_apply_fwd(const Args& a, const Dyn& d, cudaStream_t stream);
+cudaError_t launch_apply_bwd(const Args& a, cudaStream_t stream);
 int mega_ring_bytes();
 struct EvalParams {
   const float* pred; const float* gt; const float* mean; const float* stddev; const int32_t* action;
@@ -258,6 +260,7 @@ struct b200_plan {
   bool large;
   int sms;
   int cg = 1;                // CTAs per MMA: 2 = CTA pairs (large-batch plans), 1 otherwise
+  bool split_ew = false;     // large bf16 plans: the BatchNorm apply passes run as high-occupancy kernels of their own
   bool helpers = false;      // CTA pairs + helper warps: apply passes overlap the GEMM that consumes them (mega_pairx.cu)
   int variant() const { return helpers ? 3 : cg; }
   int workers() const { return sms / cg; }
@@ -354,6 +357,20 @@ static int end_phase(b200_plan* pl) {
         if (chunk[a.id] != chunk[b.id]) return chunk[a.id] < chunk[b.id];
         return a.cost > b.cost;
       });
+    } else if (p.num_gemm == 2 && pl->large && !(getenv("B200_INTERLEAVE") && atoi(getenv("B200_INTERLEAVE")) == 0)) {
+      // Two jobs in one phase = a dgrad GEMM (short mainloop, heavy epilogue: z / residual / keep rows in, dy or g
+      // out) next to a wgrad GEMM (K slices with a mainloop twice as long and an epilogue that is a handful of vector
+      // reductions).  Longest-first puts every wgrad slice in front and leaves each CTA a run of dgrad tiles whose
+      // epilogues (13 us) cannot hide behind their own mainloops (4.3 us).  Interleaved by relative position --
+      // about two dgrad tiles per wgrad slice on every CTA -- the dgrad epilogue of one tile runs under the wgrad
+      // mainloop of the next (measured: 280 / 315 us -> 235 / 260 us per phase at batch 65 536).
+      std::vector<double> key(tiles.size());
+      int id2 = 0;
+      for (int j = 0; j < p.num_gemm; ++j) {
+        const GemmJob& g = pl->cur.gj[j];
+        for (int t = 0; t < g.num_tiles; ++t, ++id2) key[id2] = (double(t) + 0.5) / double(g.num_tiles);
+      }
+      std::stable_sort(tiles.begin(), tiles.end(), [&](const T& a, const T& b) { return key[a.id] < key[b.id]; });
     } else {
       std::stable_sort(tiles.begin(), tiles.end(), [](const T& a, const T& b) { return a.cost > b.cost; });
     }
@@ -908,18 +925,18 @@ static int build_plan(b200_plan* pl) {
   return 0;
 }
 
-static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, cudaStream_t stream) {
-  if (count <= 0) return fail("empty schedule (plan kind does not support this call)");
+// One launch of the persistent kernel over phases [first, first + count) of the plan.
+static int run_phases(b200_plan* pl, int first, int count, const Dyn& dyn, cudaStream_t stream) {
   MegaParams p;
   memset(&p, 0, sizeof p);
-  p.blobs = pl->u.blobs + s.first;
-  p.cta_tiles = pl->u.cta_tiles + size_t(s.first) * pl->workers();
+  p.blobs = pl->u.blobs + first;
+  p.cta_tiles = pl->u.cta_tiles + size_t(first) * pl->workers();
   p.tmaps = pl->u.tmaps;
   p.sched = pl->u.sched;
   p.adam = (pl->d.exp_avg && pl->d.exp_avg_sq) ? pl->u.adam_tab : nullptr;
   p.barrier = pl->u.barrier;
   p.phase_ns = pl->u.phase_ns;
-  pl->last_first = s.first; pl->last_count = count;
+  pl->last_first = first; pl->last_count = count;
   p.num_phases = count;
   static const uint32_t dbg = getenv("B200_DBG") ? uint32_t(atoi(getenv("B200_DBG"))) : 0u;
   p.dbg = dbg;
@@ -933,6 +950,30 @@ static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, c
   pl->bar_count += uint32_t(grid) * uint32_t(count - 1);
   CK(launch_mega(p, grid, coop, stream, pl->variant()));
   g_launches.fetch_add(1);
+  return 0;
+}
+
+// A phase that is nothing but one large-batch bf16 apply pass (classic builds): runs as a kernel of its own.
+static bool is_split_apply(const b200_plan* pl, const PhaseBlob& b) {
+  if (!pl->split_ew || b.ph.num_gemm != 0 || b.ph.num_ew != 1 || b.ej[0].a.planes != 1) return false;
+  return b.ej[0].kind == EW_BN_FWD_APPLY || b.ej[0].kind == EW_BN_BWD_APPLY;
+}
+
+static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, cudaStream_t stream) {
+  if (count <= 0) return fail("empty schedule (plan kind does not support this call)");
+  // Stream order replaces the grid barrier on both sides of a split-out apply pass; the phases in between go to the
+  // persistent kernel together (one cooperative launch per run of phases).
+  int seg = s.first;
+  for (int i = s.first; i < s.first + count; ++i) {
+    const PhaseBlob& b = pl->blobs[i];
+    if (!is_split_apply(pl, b)) continue;
+    if (i > seg && run_phases(pl, seg, i - seg, dyn, stream)) return 1;
+    if (b.ej[0].kind == EW_BN_FWD_APPLY) CK(launch_apply_fwd(b.ej[0].a, dyn, stream));
+    else CK(launch_apply_bwd(b.ej[0].a, stream));
+    g_launches.fetch_add(1);
+    seg = i + 1;
+  }
+  if (s.first + count > seg && run_phases(pl, seg, s.first + count - seg, dyn, stream)) return 1;
   return 0;
 }
 
@@ -1022,6 +1063,8 @@ int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
   // of a training plan overlap the GEMM that consumes their output (mega_pairx.cu; measured in DESIGN.md section 8).
   pl->helpers = pl->cg == 2 && getenv("B200_HELPERS") && atoi(getenv("B200_HELPERS")) == 1 &&
                 mega_pairx_max_clusters(pl->sms) >= pl->sms / 2;
+  // B200_SPLIT_EW=0 keeps the apply passes inside the persistent kernel (per-phase time stamps, A/B comparison)
+  pl->split_ew = pl->large && pl->P == 1 && !pl->helpers && !(getenv("B200_SPLIT_EW") && atoi(getenv("B200_SPLIT_EW")) == 0);
   Carver c(desc->workspace);
   carve(c, pl->u, pl->B, pl->P, pl->kind);
   if (build_plan(pl)) { delete pl; return 1; }
