@@ -3,6 +3,10 @@ import os
 import sys
 import warnings
 
+# per-phase %globaltimer stamps describe ONE launch of the persistent kernel: keep the large-batch apply passes inside
+# it for this script (by default they run as kernels of their own between launches, csrc/api.cu run_sched)
+os.environ.setdefault("B200_SPLIT_EW", "0")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
