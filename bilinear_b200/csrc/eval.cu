@@ -13,7 +13,8 @@
 //     characteristic quartic (the QCP method), eigenvector from the adjugate -- scale, aligned
 //     distances.  Degenerate poses (repeated top eigenvalue, zero extent) fall back to a cyclic
 //     Jacobi eigen-solver / the unaligned distance, so the result is always finite.
-//   - per-action sums are accumulated in fp64 in shared memory and flushed once per CTA.
+//   - per-action sums are staged in fp32 shared-memory buckets per chunk, collected into fp64 per-CTA totals and
+//     flushed with one double atomic per action per CTA.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -240,27 +241,43 @@ __device__ __forceinline__ void pose_metrics(float* P, float* G, float& dist, fl
   }
 }
 
-// Per-action accumulation (valid_bilinear.py:61-70) without contended atomics: the warp walks over the
-// distinct action ids it holds; for each, the lanes of that action are summed with shuffles (fp64, like
-// the reference's np.double accumulation) and ONE lane adds the result to the warp's private buckets.
+// Per-action accumulation (valid_bilinear.py:61-70) staged through shared memory.  Every pose adds its two fp32
+// results and a count to the CTA's staging buckets with native shared-memory atomics (3 instructions per pose, a
+// few-way conflict among the 32 lanes); once per chunk, right behind the barrier the chunk loop has anyway, thread a
+// moves bucket a -- the fp32 sum of at most a couple of hundred values -- into its float64 accumulator with an
+// atomic exchange (read-and-clear: an add that arrives later simply stays for the next round).  The float64 totals
+// leave the CTA once, at the end.  This replaced (i) a second kernel re-reading the per-pose results (11-18 us of
+// kernel plus ~18 us of launch gap on a 62 us pass) and (ii) warp-shuffle reductions per bucket (+24-29 us).
+struct ActionStage {
+  float s[kMaxActions], ps[kMaxActions];
+  unsigned int c[kMaxActions];
+};
+struct ActionTotals {
+  double s = 0.0, ps = 0.0;
+  unsigned long long c = 0ull;
+};
 template <bool DO_M, bool DO_P>
-__device__ __forceinline__ void warp_accumulate(bool valid, int act, float dist, float pdist, double* wS, double* wPS,
-                                                unsigned long long* wC, int lane) {
-  uint32_t todo = __ballot_sync(0xffffffffu, valid);
-  while (todo) {
-    const int leader = __ffs(todo) - 1;
-    const int a = __shfl_sync(0xffffffffu, act, leader);
-    const bool mine = valid && act == a;
-    const uint32_t m = __ballot_sync(0xffffffffu, mine);
-    double s = (DO_M && mine) ? double(dist) : 0.0, ps = (DO_P && mine) ? double(pdist) : 0.0;
-    if (DO_M) s = warp_sum(s);
-    if (DO_P) ps = warp_sum(ps);
-    if (lane == leader) {
-      if (DO_M) wS[a] += s;
-      if (DO_P) wPS[a] += ps;
-      wC[a] += (unsigned long long)__popc(m);
-    }
-    todo &= ~m;
+__device__ __forceinline__ void stage_add(ActionStage& st, int act, float dist, float pdist) {
+  if (DO_M) atomicAdd(&st.s[act], dist);
+  if (DO_P) atomicAdd(&st.ps[act], pdist);
+  atomicAdd(&st.c[act], 1u);
+}
+template <bool DO_M, bool DO_P>
+__device__ __forceinline__ void stage_collect(ActionStage& st, ActionTotals& tot, int tid, int n_actions) {
+  if (tid < n_actions) {
+    if (DO_M) tot.s += double(atomicExch(&st.s[tid], 0.f));
+    if (DO_P) tot.ps += double(atomicExch(&st.ps[tid], 0.f));
+    tot.c += atomicExch(&st.c[tid], 0u);
+  }
+}
+template <bool DO_M, bool DO_P>
+__device__ __forceinline__ void stage_flush(ActionStage& st, ActionTotals& tot, const EvalParams& prm, int tid) {
+  __syncthreads();   // the last chunk's adds are in
+  stage_collect<DO_M, DO_P>(st, tot, tid, prm.n_actions);
+  if (tid < prm.n_actions && tot.c != 0ull) {
+    if (DO_M && prm.acc_sum) atomicAdd(prm.acc_sum + tid, tot.s);
+    if (DO_P && prm.pacc_sum) atomicAdd(prm.pacc_sum + tid, tot.ps);
+    if (prm.acc_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(prm.acc_cnt) + tid, tot.c);
   }
 }
 
@@ -274,10 +291,10 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams prm
   float* sG = sm + CH * PITCH;
   float* sMean = sG + CH * PITCH;
   float* sStd = sMean + W;
-  __shared__ double accS[kEvalThreads / 32][kMaxActions], accPS[kEvalThreads / 32][kMaxActions];
-  __shared__ unsigned long long accC[kEvalThreads / 32][kMaxActions];
+  __shared__ ActionStage stage;
+  ActionTotals tot;
   const int tid = threadIdx.x;
-  for (int i = tid; i < (kEvalThreads / 32) * kMaxActions; i += CH) { (&accS[0][0])[i] = 0.0; (&accPS[0][0])[i] = 0.0; (&accC[0][0])[i] = 0ull; }
+  for (int i = tid; i < kMaxActions; i += CH) { stage.s[i] = 0.f; stage.ps[i] = 0.f; stage.c[i] = 0u; }
   const bool unnorm = prm.mean != nullptr;
   for (int i = tid; i < W; i += CH) {
     sMean[i] = unnorm ? prm.mean[i] : 0.f;
@@ -349,21 +366,12 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams prm
         act = prm.action ? prm.action[gi] : 0;
         act = min(max(act, 0), prm.n_actions - 1);
       }
-      const int wi = tid >> 5;
-      warp_accumulate<DO_M, DO_P>(valid, act, dist, pdist, accS[wi], accPS[wi], accC[wi], tid & 31);
+      if (valid) stage_add<DO_M, DO_P>(stage, act, dist, pdist);
     }
     __syncthreads();
+    stage_collect<DO_M, DO_P>(stage, tot, tid, prm.n_actions);
   }
-  for (int i = tid; i < prm.n_actions; i += CH) {
-    double sm = 0.0, ps = 0.0;
-    unsigned long long c = 0ull;
-    for (int w = 0; w < kEvalThreads / 32; ++w) { sm += accS[w][i]; ps += accPS[w][i]; c += accC[w][i]; }
-    if (c != 0ull) {
-      if (DO_M && prm.acc_sum) atomicAdd(prm.acc_sum + i, sm);
-      if (DO_P && prm.pacc_sum) atomicAdd(prm.pacc_sum + i, ps);
-      if (prm.acc_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(prm.acc_cnt) + i, c);
-    }
-  }
+  stage_flush<DO_M, DO_P>(stage, tot, prm, tid);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -373,7 +381,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams prm
 // buffer: as soon as every thread holds its pose in registers the buffer is handed back to the TMA
 // unit for the next chunk, which lands while the per-pose math runs -- 4 CTAs (16 warps) per SM hide
 // the serial parts of the Procrustes solve, and no data passes through registers on its way into
-// shared memory.  Per-action sums: see action_reduce_kernel (two-kernel scheme) or, when the caller
+// shared memory.  Per-action sums: staged through shared-memory fp32 buckets (stage_add); when the caller
 // keeps no per-pose output, the in-kernel warp walk.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTmaPoses = kEvalThreads;             // poses per chunk
@@ -389,14 +397,10 @@ eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_consta
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   __shared__ uint64_t full;
   __shared__ float sMean[W], sStd[W];
-  __shared__ double accS[ACC ? kEvalThreads / 32 : 1][ACC ? kMaxActions : 1], accPS[ACC ? kEvalThreads / 32 : 1][ACC ? kMaxActions : 1];
-  __shared__ unsigned long long accC[ACC ? kEvalThreads / 32 : 1][ACC ? kMaxActions : 1];
+  __shared__ ActionStage stage;
+  ActionTotals tot;
   const int tid = threadIdx.x;
-  if (ACC) {
-    for (int i = tid; i < (kEvalThreads / 32) * kMaxActions; i += kEvalThreads) {
-      (&accS[0][0])[i] = 0.0; (&accPS[0][0])[i] = 0.0; (&accC[0][0])[i] = 0ull;
-    }
-  }
+  for (int i = tid; i < kMaxActions; i += kEvalThreads) { stage.s[i] = 0.f; stage.ps[i] = 0.f; stage.c[i] = 0u; }
   const bool unnorm = prm.mean != nullptr;
   for (int i = tid; i < W; i += kEvalThreads) {
     sMean[i] = unnorm ? prm.mean[i] : 0.f;
@@ -436,6 +440,7 @@ eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_consta
       }
     }
     __syncthreads();   // every thread holds its pose: the buffer goes back to the TMA unit
+    if (ACC) stage_collect<DO_M, DO_P>(stage, tot, tid, prm.n_actions);   // (the previous chunk's adds are all in)
     if (tid == 0 && ch + gridDim.x < nchunks) {
       fence_proxy_async_all();
       issue(ch + gridDim.x);
@@ -466,86 +471,11 @@ eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_consta
       if (ACC) {
         act = prm.action ? prm.action[gi] : 0;
         act = min(max(act, 0), prm.n_actions - 1);
-      }
-    }
-    if (ACC) {
-      const int wi = tid >> 5;
-      warp_accumulate<DO_M, DO_P>(valid, act, dist, pdist, accS[wi], accPS[wi], accC[wi], tid & 31);
-    }
-  }
-  if (ACC) {
-    __syncthreads();
-    for (int i = tid; i < prm.n_actions; i += kEvalThreads) {
-      double sm = 0.0, ps = 0.0;
-      unsigned long long c = 0ull;
-      for (int w = 0; w < kEvalThreads / 32; ++w) { sm += accS[w][i]; ps += accPS[w][i]; c += accC[w][i]; }
-      if (c != 0ull) {
-        if (DO_M && prm.acc_sum) atomicAdd(prm.acc_sum + i, sm);
-        if (DO_P && prm.pacc_sum) atomicAdd(prm.pacc_sum + i, ps);
-        if (prm.acc_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(prm.acc_cnt) + i, c);
+        stage_add<DO_M, DO_P>(stage, act, dist, pdist);
       }
     }
   }
-}
-
-// Second kernel of the two-kernel scheme (valid_bilinear.py:61-70): per-action fp64 sums of the per-pose
-// results.  Reads 4 B (action) + 4 / 8 B (per-pose sums) per pose; every thread keeps private fp64
-// buckets in registers (NA <= 16: predicated adds, no atomics, no shuffles in the loop).
-constexpr int kRedThreads = 512;
-constexpr int kRedNA = 16;
-template <bool DO_M, bool DO_P>
-__global__ void __launch_bounds__(kRedThreads) action_reduce_kernel(const EvalParams prm) {
-  double s[kRedNA], ps[kRedNA];
-  unsigned int c[kRedNA];
-#pragma unroll
-  for (int a = 0; a < kRedNA; ++a) { s[a] = 0.0; ps[a] = 0.0; c[a] = 0u; }
-  const int64_t stride = int64_t(gridDim.x) * kRedThreads;
-  constexpr int U = 4;   // four poses per thread in flight
-  for (int64_t i0 = int64_t(blockIdx.x) * kRedThreads + threadIdx.x; i0 < prm.n; i0 += U * stride) {
-    int act[U];
-    float d[U], pd[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t i = min(i0 + u * stride, prm.n - 1);   // clamped; out-of-range slots are discarded below
-      act[u] = prm.action ? __ldcs(prm.action + i) : 0;
-      d[u] = DO_M ? __ldcs(prm.dist_out + i) : 0.f;
-      pd[u] = DO_P ? __ldcs(prm.pdist_out + i) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int au = (i0 + u * stride < prm.n) ? min(max(act[u], 0), prm.n_actions - 1) : -1;
-      const double dd = double(d[u]), pdd = double(pd[u]);
-#pragma unroll
-      for (int a = 0; a < kRedNA; ++a) {
-        const bool m = au == a;
-        if (DO_M) s[a] += m ? dd : 0.0;
-        if (DO_P) ps[a] += m ? pdd : 0.0;
-        c[a] += m ? 1u : 0u;
-      }
-    }
-  }
-  __shared__ double bs[kRedThreads / 32][kRedNA], bps[kRedThreads / 32][kRedNA];
-  __shared__ unsigned long long bc[kRedThreads / 32][kRedNA];
-  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int a = 0; a < kRedNA; ++a) {
-    const double ws = DO_M ? warp_sum(s[a]) : 0.0, wps = DO_P ? warp_sum(ps[a]) : 0.0;
-    unsigned int wc = c[a];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wc += __shfl_xor_sync(0xffffffffu, wc, o);
-    if (lane == 0) { bs[wi][a] = ws; bps[wi][a] = wps; bc[wi][a] = wc; }
-  }
-  __syncthreads();
-  if (threadIdx.x < prm.n_actions && threadIdx.x < kRedNA) {
-    double sm = 0.0, psm = 0.0;
-    unsigned long long cc = 0ull;
-    for (int w = 0; w < kRedThreads / 32; ++w) { sm += bs[w][threadIdx.x]; psm += bps[w][threadIdx.x]; cc += bc[w][threadIdx.x]; }
-    if (cc != 0ull) {
-      if (DO_M && prm.acc_sum) atomicAdd(prm.acc_sum + threadIdx.x, sm);
-      if (DO_P && prm.pacc_sum) atomicAdd(prm.pacc_sum + threadIdx.x, psm);
-      if (prm.acc_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(prm.acc_cnt) + threadIdx.x, cc);
-    }
-  }
+  if (ACC) stage_flush<DO_M, DO_P>(stage, tot, prm, tid);
 }
 
 template <bool DO_M, bool DO_P, bool ACC>
@@ -563,11 +493,6 @@ static cudaError_t launch_eval_tma_t(const EvalParams& prm, const CUtensorMap& t
   const int64_t nchunks = (prm.n + kTmaPoses - 1) / kTmaPoses;
   const int grid = int(std::max<int64_t>(1, std::min<int64_t>(nchunks, int64_t(sms) * 4)));
   eval_kernel_tma<DO_M, DO_P, ACC><<<grid, kEvalThreads, smem, stream>>>(tp, tg, prm);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess || ACC) return e;
-  // one CTA per SM: the final 3 x 15 double atomics per CTA all hit the same 45 addresses
-  const int rgrid = int(std::max<int64_t>(1, std::min<int64_t>((prm.n + kRedThreads - 1) / kRedThreads, int64_t(sms))));
-  action_reduce_kernel<DO_M, DO_P><<<rgrid, kRedThreads, 0, stream>>>(prm);
   return cudaGetLastError();
 }
 
@@ -575,15 +500,8 @@ static cudaError_t launch_eval_tma_t(const EvalParams& prm, const CUtensorMap& t
 // the caller, api.cu); J = 16 only.
 cudaError_t launch_eval_tma(const EvalParams& prm, const CUtensorMap* tp, const CUtensorMap* tg, bool do_m, bool do_p,
                             cudaStream_t stream, int* launches) {
-  // two-kernel scheme when the per-pose results the caller keeps are enough to rebuild the per-action
-  // sums (and there are at most 16 buckets); otherwise the sums are taken inside the kernel
-  const bool two = prm.n_actions <= kRedNA && (!do_m || prm.dist_out) && (!do_p || prm.pdist_out);
-  *launches = two ? 2 : 1;
-  if (two) {
-    if (do_m && do_p) return launch_eval_tma_t<true, true, false>(prm, *tp, *tg, stream);
-    if (do_m) return launch_eval_tma_t<true, false, false>(prm, *tp, *tg, stream);
-    return launch_eval_tma_t<false, true, false>(prm, *tp, *tg, stream);
-  }
+  // one kernel: per-pose results (when the caller keeps them) and the per-action float64 sums in the same pass
+  *launches = 1;
   if (do_m && do_p) return launch_eval_tma_t<true, true, true>(prm, *tp, *tg, stream);
   if (do_m) return launch_eval_tma_t<true, false, true>(prm, *tp, *tg, stream);
   return launch_eval_tma_t<false, true, true>(prm, *tp, *tg, stream);
