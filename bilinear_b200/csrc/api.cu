@@ -25,6 +25,7 @@ int mega_pair_max_clusters(int grid);
 int mega_pairx_max_clusters(int grid);
 cudaError_t launch_apply_fwd(const Args& a, const Dyn& d, cudaStream_t stream);
 cudaError_t launch_apply_bwd(const Args& a, cudaStream_t stream);
+cudaError_t launch_dgrad_stats(const Args& a, cudaStream_t stream);
 int mega_ring_bytes();
 struct EvalParams {
   const float* pred; const float* gt; const float* mean; const float* stddev; const int32_t* action;
@@ -98,6 +99,26 @@ static int encode_map(CUtensorMap* out, const void* base, int64_t inner, int64_t
   return 0;
 }
 
+// Output map of a bf16 large-batch epilogue (Args::tm_out): feature-major [rows][inner] tensor, box = 32 entries
+// (64 bytes) x 32 rows, 64-byte swizzle -- the staging tile stage_store32_bf16 (mega.cu) fills.
+static int encode_out_map(CUtensorMap* out, const void* base, int64_t inner, int64_t rows, int64_t ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cuuint64_t(inner), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(ld) * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  if ((strides[0] % 16) || (reinterpret_cast<uintptr_t>(base) % 16))
+    return fail("output tensor map alignment: ld=%lld base=%p", (long long)ld, base);
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled (output) -> %d (inner=%lld rows=%lld ld=%lld)", int(r), (long long)inner,
+                (long long)rows, (long long)ld);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // flat parameter layout (order of BilinearUnit.parameters(), model/bilinear.py:22-29)
 // ------------------------------------------------------------------------------------------------
@@ -135,7 +156,7 @@ struct Carver {
   template <class T> T* take_n(int64_t n) { return reinterpret_cast<T*>(take(n * int64_t(sizeof(T)))); }
 };
 
-constexpr int kMaxTmaps = 128, kMaxPhases = 160, kMaxCtas = 192;
+constexpr int kMaxTmaps = 192, kMaxPhases = 160, kMaxCtas = 192;
 constexpr int kMaxSched = 1 << 18;   // int32 entries of per-phase tile schedules
 constexpr int kSmallSplit = 16;      // K slices of the small-batch GEMMs (K = 1024 -> one k-block each)
 
@@ -252,6 +273,9 @@ static int64_t carve(Carver& c, Bufs& u, int B, int P, int kind) {
 // plan
 // ------------------------------------------------------------------------------------------------
 struct Sched { int first = 0, count = 0; };
+#ifndef B200_BLOCKED
+#define B200_BLOCKED 0
+#endif
 
 struct b200_plan {
   b200_plan_desc d;
@@ -261,6 +285,8 @@ struct b200_plan {
   int sms;
   int cg = 1;                // CTAs per MMA: 2 = CTA pairs (large-batch plans), 1 otherwise
   bool split_ew = false;     // large bf16 plans: the BatchNorm apply passes run as high-occupancy kernels of their own
+  int tma_store = 0;         // large bf16 plans: epilogue rows leave through shared-memory staging tiles + TMA stores
+                             // (bit 0: forward z, bit 1: dgrad g / dy)
   bool helpers = false;      // CTA pairs + helper warps: apply passes overlap the GEMM that consumes them (mega_pairx.cu)
   int variant() const { return helpers ? 3 : cg; }
   int workers() const { return sms / cg; }
@@ -302,7 +328,10 @@ static int end_phase(b200_plan* pl) {
     sb = std::max(sb, g.a.planes * (128 * 128 + (g.BN / pl->cg) * 128));
   }
   p.stage_bytes = sb;
-  p.num_stages = std::max(1, std::min(8, mega_ring_bytes() / sb));
+  int ring = mega_ring_bytes();
+  for (int j = 0; j < p.num_gemm; ++j)
+    if (pl->cur.gj[j].a.tm_out) ring = mega_ring_bytes() - kEpiStageBytes;   // epilogue staging tiles sit at the top
+  p.num_stages = std::max(1, std::min(8, ring / sb));
   p.aux_off = -1;
   if (pl->helpers && p.num_ew > 0) {
     // the apply pass keeps its per-feature constants in the part of the ring region the operand stages leave free
@@ -438,6 +467,17 @@ static int add_gemm(b200_plan* pl, const PlaneRef& A, int a_mn, const PlaneRef& 
   g.gate_kind = gate ? gate_kind : GATE_NONE;
   g.gate = gate;
   g.a = a;
+  g.a.tm_out = nullptr;
+  if (a.planes == 1 && M % 128 == 0 &&
+      ((epi == EPI_FWD_LARGE && (pl->tma_store & 1)) || (epi == EPI_DGRAD_LARGE && (pl->tma_store & 2)))) {
+    // the epilogue's output rows leave through a staging tile and the TMA unit (Args::tm_out)
+    void* dst = (epi == EPI_FWD_LARGE) ? a.zT : (a.g_out ? a.g_out : a.dyT);
+    if (int(pl->tm.size()) >= kMaxTmaps) return fail("too many tensor maps");
+    CUtensorMap m;
+    if (encode_out_map(&m, dst, a.ldT, M, a.ldT)) return 1;
+    pl->tm.push_back(m);
+    g.a.tm_out = pl->u.tmaps + (pl->tm.size() - 1);
+  }
   pl->cur.gj[pl->cur.ph.num_gemm++] = g;
   return 0;
 }
@@ -634,7 +674,8 @@ static int build_decode(b200_plan* pl, bool fuse_loss, bool train) {
 static int wgrad_split(const b200_plan* pl) {
   if (!pl->large) return 1;
   const int num_kb = (pl->B + 63) / 64;
-  return std::max(1, num_kb / 32);
+  static const int slice_kb = getenv("B200_WGRAD_SLICE") ? std::max(8, atoi(getenv("B200_WGRAD_SLICE"))) : 32;   // A/B switch
+  return std::max(1, num_kb / slice_kb);
 }
 
 // backward phases (autograd of model/bilinear.py:31-41): for l = 4..0 { dgrad(l+1 -> l) with the
@@ -647,6 +688,7 @@ static int build_backward(b200_plan* pl, bool with_norm, const Args* tail_ew, in
   const int B = pl->B;
   const int wsplit = wgrad_split(pl);
   double* wnorm = (with_norm && wsplit == 1) ? u.gnorm2 : nullptr;   // split-K: EW_SUMSQ over everything instead
+  static const bool thin_off = getenv("B200_THIN_STATS") && atoi(getenv("B200_THIN_STATS")) == 0;   // A/B switch
   auto layer_args = [&](int l) {
     Args a = base_args(pl, l);
     a.gamma = d.params + kPL.g[l];
@@ -700,6 +742,7 @@ static int build_backward(b200_plan* pl, bool with_norm, const Args* tail_ew, in
     const int up = l + 1;                      // the Linear whose input is h_l
     const int Kd = kPL.rows[up];               // 1024, or 48 for decode
     const PlaneRef& dzu = (up == 5) ? u.dP_fm : u.dz_fm[up];
+    const bool thin = pl->split_ew && up == 5 && a.g_out != nullptr && !thin_off;
     begin_phase(pl);
     if (!pl->large && prefetch_opt) {
       pl->cur.ph.pf_slice = 4 - l;
@@ -718,6 +761,11 @@ static int build_backward(b200_plan* pl, bool with_norm, const Args* tail_ew, in
         a.out_fm = PlaneRef{nullptr, 0, 0};
         a.loss_acc = with_norm ? u.loss_acc : nullptr;
       }
+    } else if (thin) {
+      // the K = 48 dgrad stores the raw total gradient only (epi_dgrad_raw_bf16); EW_DGRAD_STATS follows
+      Args r = a;
+      r.stats = nullptr;
+      if (add_gemm(pl, u.W[up], 1, dzu, 1, kHidden, B, Kd, tile_bn(pl, B), EPI_DGRAD_LARGE, r)) return 1;
     } else {
       if (add_gemm(pl, u.W[up], 1, dzu, 1, kHidden, B, Kd, tile_bn(pl, B), EPI_DGRAD_LARGE, a)) return 1;
     }
@@ -730,6 +778,11 @@ static int build_backward(b200_plan* pl, bool with_norm, const Args* tail_ew, in
         return 1;
     }
     if (end_phase(pl)) return 1;
+    if (thin) {
+      begin_phase(pl);
+      if (add_ew(pl, EW_DGRAD_STATS, a)) return 1;
+      if (end_phase(pl)) return 1;
+    }
     begin_phase(pl);
     if (add_ew(pl, pl->large ? EW_BN_BWD_APPLY : EW_BN_BWD_SMALL, a)) return 1;
     if (end_phase(pl)) return 1;
@@ -956,7 +1009,7 @@ static int run_phases(b200_plan* pl, int first, int count, const Dyn& dyn, cudaS
 // A phase that is nothing but one large-batch bf16 apply pass (classic builds): runs as a kernel of its own.
 static bool is_split_apply(const b200_plan* pl, const PhaseBlob& b) {
   if (!pl->split_ew || b.ph.num_gemm != 0 || b.ph.num_ew != 1 || b.ej[0].a.planes != 1) return false;
-  return b.ej[0].kind == EW_BN_FWD_APPLY || b.ej[0].kind == EW_BN_BWD_APPLY;
+  return b.ej[0].kind == EW_BN_FWD_APPLY || b.ej[0].kind == EW_BN_BWD_APPLY || b.ej[0].kind == EW_DGRAD_STATS;
 }
 
 static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, cudaStream_t stream) {
@@ -969,6 +1022,7 @@ static int run_sched(b200_plan* pl, const Sched& s, int count, const Dyn& dyn, c
     if (!is_split_apply(pl, b)) continue;
     if (i > seg && run_phases(pl, seg, i - seg, dyn, stream)) return 1;
     if (b.ej[0].kind == EW_BN_FWD_APPLY) CK(launch_apply_fwd(b.ej[0].a, dyn, stream));
+    else if (b.ej[0].kind == EW_DGRAD_STATS) CK(launch_dgrad_stats(b.ej[0].a, stream));
     else CK(launch_apply_bwd(b.ej[0].a, stream));
     g_launches.fetch_add(1);
     seg = i + 1;
@@ -1004,9 +1058,6 @@ __global__ void unblock_keep_kernel(const uint32_t* __restrict__ src, uint32_t* 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kHidden * ldw) return;
   const int f = i / ldw, w = i - f * ldw;
-#ifndef B200_BLOCKED
-#define B200_BLOCKED 0
-#endif
 #if B200_BLOCKED
   dst[i] = src[((int64_t(f >> 5) * ldw + w) << 5) + (f & 31)];
 #else
@@ -1065,6 +1116,13 @@ int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
                 mega_pairx_max_clusters(pl->sms) >= pl->sms / 2;
   // B200_SPLIT_EW=0 keeps the apply passes inside the persistent kernel (per-phase time stamps, A/B comparison)
   pl->split_ew = pl->large && pl->P == 1 && !pl->helpers && !(getenv("B200_SPLIT_EW") && atoi(getenv("B200_SPLIT_EW")) == 0);
+  // B200_TMA_STORE=<mask> (experiment, off by default).  Measured at batch 65536: inside one persistent launch the
+  // forward GEMM phases lose 4.5 us each with staged TMA stores of z and the dgrad phases GAIN 3 .. 14 us with staged
+  // stores of g / dy; with the apply passes split out (the default) the step time does not move either way, and the
+  // epilogue-bound thin phases (K = 32 / 48) stay as long as they were -- their epilogues do not wait for the
+  // load/store unit.
+  pl->tma_store = (pl->large && pl->P == 1 && !pl->helpers && !B200_BLOCKED && getenv("B200_TMA_STORE"))
+                      ? (atoi(getenv("B200_TMA_STORE")) & 3) : 0;
   Carver c(desc->workspace);
   carve(c, pl->u, pl->B, pl->P, pl->kind);
   if (build_plan(pl)) { delete pl; return 1; }

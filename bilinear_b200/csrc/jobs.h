@@ -56,6 +56,7 @@ enum EwKind : int32_t {
   EW_DECODE_SMALL = 11,// small path: sum partials + bias -> p; optional MSE loss, dP planes, decode bias grad
   EW_COMM_BARRIER = 12,// data parallel: cross-GPU barrier through flags in peer memory (block 0 only)
   EW_ALLREDUCE = 13,   // data parallel: reduce-scatter + all-gather of the flat gradient over NVLink peer memory
+  EW_DGRAD_STATS = 14, // split large bf16 plans: sums of dy, dy*xhat from the raw gradient a thin dgrad GEMM stored
 };
 
 // bf16 "plane" tensor: value = sum_p plane[p].  planes = 1 (bf16 mode) or 3 (fp32-parity mode:
@@ -205,7 +206,13 @@ struct alignas(16) Args {
   // chunk before the next chunk, and counts finished (feature, chunk) items in gate[chunk]; GEMM tiles whose
   // operand lies in that chunk start once the counter reaches kHidden (GemmJob::gate)
   uint32_t* gate;          // EW_BN_FWD_APPLY / EW_BN_BWD_APPLY: per-chunk arrival counters (nullptr: no consumer waits)
+  // ---- bf16 large-batch GEMM epilogues: tensor map (device address; box = 32 entries x 32 feature rows, 64-byte
+  // swizzle) of the feature-major tensor the epilogue writes -- z (EPI_FWD_LARGE), g / dy (EPI_DGRAD_LARGE).  An
+  // epilogue thread owns one feature row: its 64-byte runs go through a shared-memory staging tile and out with
+  // ONE TMA store per warp and chunk instead of 32 two-sector requests through the load/store unit.  nullptr: direct stores.
+  const void* tm_out;
 };
+constexpr int kEpiStageBytes = 16 * 1024;   // 4 epilogue warps x 2 staging tiles x 2 KB, at the top of the ring region
 
 struct alignas(16) GemmJob {
   int32_t tmap_a, tmap_b;  // indices into the tensor-map table

@@ -27,3 +27,13 @@ for _ in range(iters):
     loss, gn = net.train_step(opt, x, y)
 torch.cuda.synchronize()
 print("ok loss %.5f gnorm %.4f" % (float(loss), float(gn)))
+if os.environ.get("B200_TIME"):      # B200_TIME=n: n more iterations, event-timed one by one (A/B runs of build switches)
+    n = int(os.environ["B200_TIME"])
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    ev[0].record()
+    for i in range(n):
+        net.train_step(opt, x, y)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    us = sorted(ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(n))
+    print("step time: median %.1f us, min %.1f us, max %.1f us over %d iterations" % (us[n // 2], us[0], us[-1], n))

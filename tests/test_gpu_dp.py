@@ -40,7 +40,7 @@ def test_data_parallel_step_matches_per_shard_reference(cuda_lib, variant):
     with open(os.path.join(log_dir, "dp_check_%s_%dgpu.log" % (variant, n)), "w") as f:
         f.write(r.stdout + "\n--- stderr ---\n" + r.stderr[-4000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    lines = [l for l in r.stdout.splitlines() if "-> OK" in l]
-    assert len(lines) == n, r.stdout[-3000:]
-    assert all(("[%s]" % variant) in l for l in lines)
+    # ranks share one pipe and their lines may run together: count the markers, not the lines
+    assert r.stdout.count("-> OK") == n, r.stdout[-3000:]
+    assert r.stdout.count("[%s] rank" % variant) == n  and "-> FAIL" not in r.stdout, r.stdout[-3000:]
     assert r.stdout.count("parameters identical across ranks: True") == n
