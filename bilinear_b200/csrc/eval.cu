@@ -80,8 +80,14 @@ __device__ __noinline__ void jacobi4_top(const float* Nm, float& lam, float* q) 
   for (int k = 0; k < 4; ++k) q[k] = V[k][best];
 }
 
-// sqrt(x) for x >= 0 as x * rsqrt(x) (2 ulp; distances are ~1e1..1e3 mm and the tolerance is 0.05 mm)
-__device__ __forceinline__ float fast_sqrt(float x) { return x > 0.f ? x * rsqrtf(x) : 0.f; }
+// sqrt(x) for x >= 0: one MUFU.SQRT (sqrt.approx.ftz.f32, ~1 ulp, exact 0 for 0; distances are ~1e1..1e3 mm and the
+// tolerance is 0.05 mm).  The x * rsqrt(x) form it replaces cost a compare, a select and a multiply on top, 32 times
+// per pose.
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 __device__ __forceinline__ float det3(float a, float b, float c, float d, float e, float f, float g, float h, float i) {
   return a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
@@ -129,8 +135,23 @@ __device__ __forceinline__ void horn_top(const float S[3][3], float& lam, float 
   // eigenvector: a column of adj(N - lam I) (= const * q q^T when the top eigenvalue is simple)
   const float m00 = Nm[0] - l, m11 = Nm[5] - l, m22 = Nm[10] - l, m33 = Nm[15] - l;
   const float m01 = Nm[1], m02 = Nm[2], m03 = Nm[3], m12 = Nm[6], m13 = Nm[7], m23 = Nm[11];
-  // diagonal cofactors
+  // First column alone, when it is a good one: adj = c q q^T, so C00 = c q0^2 and |column 0|^2 = c^2 q0^2, i.e.
+  // C00^2 / |column 0|^2 = q0^2 -- the column's conditioning is known without the other three diagonals.  A pose that
+  // needs less than a ~143 degree turn (q0^2 > 0.1) is done after 4 of the 10 cofactors; everything else (and a vanishing
+  // adjugate = repeated top eigenvalue) takes the full pivoted path below.
   const float C00 = det3(m11, m12, m13, m12, m22, m23, m13, m23, m33);
+  {
+    const float C01 = -det3(m01, m12, m13, m02, m22, m23, m03, m23, m33);
+    const float C02 = det3(m01, m11, m13, m02, m12, m23, m03, m13, m33);
+    const float C03 = -det3(m01, m11, m12, m02, m12, m22, m03, m13, m23);
+    const float nn0 = C00 * C00 + C01 * C01 + C02 * C02 + C03 * C03;
+    if (nn0 > 1e-16f && C00 * C00 > 0.1f * nn0) {
+      const float r = rsqrtf(nn0);
+      q[0] = C00 * r; q[1] = C01 * r; q[2] = C02 * r; q[3] = C03 * r;
+      return;
+    }
+  }
+  // diagonal cofactors
   const float C11 = det3(m00, m02, m03, m02, m22, m23, m03, m23, m33);
   const float C22 = det3(m00, m01, m03, m01, m11, m13, m03, m13, m33);
   const float C33 = det3(m00, m01, m02, m01, m11, m12, m02, m12, m22);
@@ -236,6 +257,136 @@ __device__ __forceinline__ void pose_metrics(float* P, float* G, float& dist, fl
         const float dy = (P[3 * j + 1] + mp[1]) - (G[3 * j + 1] + mg[1]);
         const float dz = (P[3 * j + 2] + mp[2]) - (G[3 * j + 2] + mg[2]);
         pdist += fast_sqrt(dx * dx + dy * dy + dz * dz);
+      }
+    }
+  }
+}
+
+// ---- J = 16, packed-pair form of pose_metrics (TMA kernel) ------------------------------------------------------
+// sm_100 has two-wide fp32 instructions (FADD2 / FMUL2 / FFMA2 on an aligned register pair, with per-operand negation and a
+// scalar-broadcast operand form).  A pose row [x0 y0 z0 x1 y1 z1 ...] read with 128-bit shared-memory loads already sits
+// in such pairs -- (x, y), (z, x'), (y', z') for every two joints -- so everything that treats the 48 numbers alike
+// (un-normalise, centroid, centring, norms, differences) runs on 24 pairs, and the two places that mix coordinates keep
+// pair ACCUMULATORS instead: the correlation matrix as column pairs (S0b, S1b) += (px, py) * gb for even joints and
+// (S1b, S2b) += (py', pz') * gb' for odd ones (5 instead of 9 instructions per joint), the aligned residual as
+// (ax, ay) = (R00, R10) px + (R01, R11) py + (R02, R12) pz - (gx, gy) (3 + 3 instead of 12).  ncu had the scalar form at
+// 1 533 instructions per pose with the issue slots 51 % busy and DRAM at 51 %: the P-MPJPE pass was instruction-bound.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+template <bool DO_M, bool DO_P>
+__device__ __forceinline__ void pose_metrics16(float2* P, float2* G, float& dist, float& pdist) {
+  constexpr int J = 16;
+  dist = 0.f;
+  pdist = 0.f;
+  if (DO_M) {
+    float da = 0.f, db = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 d0 = sub2(P[3 * i], G[3 * i]), d1 = sub2(P[3 * i + 1], G[3 * i + 1]), d2 = sub2(P[3 * i + 2], G[3 * i + 2]);
+      const float2 q0 = mul2(d0, d0), q1 = mul2(d1, d1), q2 = mul2(d2, d2);
+      da += fast_sqrt(q0.x + q0.y + q1.x);    // valid_bilinear.py:60
+      db += fast_sqrt(q1.y + q2.x + q2.y);
+    }
+    dist = da + db;
+  }
+  if (DO_P) {
+    float2 a0 = f2(0.f, 0.f), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a0 = add2(a0, P[3 * i]); a1 = add2(a1, P[3 * i + 1]); a2 = add2(a2, P[3 * i + 2]);
+      b0 = add2(b0, G[3 * i]); b1 = add2(b1, G[3 * i + 1]); b2 = add2(b2, G[3 * i + 2]);
+    }
+    const float mpx = (a0.x + a1.y) * (1.f / J), mpy = (a0.y + a2.x) * (1.f / J), mpz = (a1.x + a2.y) * (1.f / J);
+    const float mgx = (b0.x + b1.y) * (1.f / J), mgy = (b0.y + b2.x) * (1.f / J), mgz = (b1.x + b2.y) * (1.f / J);
+    const float2 MP0 = f2(mpx, mpy), MP1 = f2(mpz, mpx), MP2 = f2(mpy, mpz);
+    const float2 MG0 = f2(mgx, mgy), MG1 = f2(mgz, mgx), MG2 = f2(mgy, mgz);
+    float2 np = f2(0.f, 0.f), ng = np;
+    float2 C0 = np, C1 = np, C2 = np, R2 = np, D0 = np, D1 = np, D2 = np, E = np;
+    float s22 = 0.f, s00 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 p0 = sub2(P[3 * i], MP0), p1 = sub2(P[3 * i + 1], MP1), p2 = sub2(P[3 * i + 2], MP2);
+      const float2 g0 = sub2(G[3 * i], MG0), g1 = sub2(G[3 * i + 1], MG1), g2 = sub2(G[3 * i + 2], MG2);
+      P[3 * i] = p0; P[3 * i + 1] = p1; P[3 * i + 2] = p2;
+      G[3 * i] = g0; G[3 * i + 1] = g1; G[3 * i + 2] = g2;
+      np = fma2(p0, p0, np); np = fma2(p1, p1, np); np = fma2(p2, p2, np);
+      ng = fma2(g0, g0, ng); ng = fma2(g1, g1, ng); ng = fma2(g2, g2, ng);
+      // even joint: p = (p0.x, p0.y, p1.x), g = (g0.x, g0.y, g1.x)
+      C0 = fma2(p0, bc2(g0.x), C0);     // (S00, S10)
+      C1 = fma2(p0, bc2(g0.y), C1);     // (S01, S11)
+      C2 = fma2(p0, bc2(g1.x), C2);     // (S02, S12)
+      R2 = fma2(bc2(p1.x), g0, R2);     // (S20, S21)
+      s22 = fmaf(p1.x, g1.x, s22);
+      // odd joint: p = (p1.y, p2.x, p2.y), g = (g1.y, g2.x, g2.y)
+      D0 = fma2(p2, bc2(g1.y), D0);     // (S10, S20)
+      D1 = fma2(p2, bc2(g2.x), D1);     // (S11, S21)
+      D2 = fma2(p2, bc2(g2.y), D2);     // (S12, S22)
+      E = fma2(bc2(p1.y), g2, E);       // (S01, S02)
+      s00 = fmaf(p1.y, g1.y, s00);
+    }
+    const float nP2 = np.x + np.y, nG2 = ng.x + ng.y;
+    float S[3][3];
+    S[0][0] = C0.x + s00;  S[0][1] = C1.x + E.x;  S[0][2] = C2.x + E.y;
+    S[1][0] = C0.y + D0.x; S[1][1] = C1.y + D1.x; S[1][2] = C2.y + D2.x;
+    S[2][0] = R2.x + D0.y; S[2][1] = R2.y + D1.y; S[2][2] = s22 + D2.y;
+    // zero-extent convention shared with oracle/pose_metrics.py (DEGENERATE_REL), as in pose_metrics
+    const float rawP2 = nP2 + float(J) * (mpx * mpx + mpy * mpy + mpz * mpz);
+    const float rawG2 = nG2 + float(J) * (mgx * mgx + mgy * mgy + mgz * mgz);
+    if (nP2 > 1e-10f * rawP2 && nG2 > 1e-10f * rawG2) {
+      const float inv = rsqrtf(nP2) * rsqrtf(nG2);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) S[a][b] *= inv;
+      float lam, q[4];
+      horn_top(S, lam, q);
+      const float scale = lam * sqrtf(nG2) * rsqrtf(nP2);   // tr * nG / nP (Appendix B)
+      const float q0 = q[0], qx = q[1], qy = q[2], qz = q[3];
+      const float s2 = 2.f * scale;
+      const float R00 = scale * (q0 * q0 + qx * qx - qy * qy - qz * qz), R01 = s2 * (qx * qy - q0 * qz),
+                  R02 = s2 * (qx * qz + q0 * qy);
+      const float R10 = s2 * (qy * qx + q0 * qz), R11 = scale * (q0 * q0 - qx * qx + qy * qy - qz * qz),
+                  R12 = s2 * (qy * qz - q0 * qx);
+      const float R20 = s2 * (qz * qx - q0 * qy), R21 = s2 * (qz * qy + q0 * qx),
+                  R22 = scale * (q0 * q0 - qx * qx - qy * qy + qz * qz);
+      const float2 U0 = f2(R00, R10), U1 = f2(R01, R11), U2 = f2(R02, R12);   // rows 0, 1 of a column
+      const float2 V0 = f2(R10, R20), V1 = f2(R11, R21), V2 = f2(R12, R22);   // rows 1, 2 of a column
+      float pa = 0.f, pb = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 p0 = P[3 * i], p1 = P[3 * i + 1], p2 = P[3 * i + 2];
+        const float2 g0 = G[3 * i], g1 = G[3 * i + 1], g2 = G[3 * i + 2];
+        float2 t = fma2(U0, bc2(p0.x), neg2(g0));
+        t = fma2(U1, bc2(p0.y), t);
+        t = fma2(U2, bc2(p1.x), t);
+        float az = fmaf(R20, p0.x, -g1.x);
+        az = fmaf(R21, p0.y, az);
+        az = fmaf(R22, p1.x, az);
+        pa += fast_sqrt(fmaf(az, az, fmaf(t.y, t.y, t.x * t.x)));
+        float2 u = fma2(V0, bc2(p1.y), neg2(g2));
+        u = fma2(V1, bc2(p2.x), u);
+        u = fma2(V2, bc2(p2.y), u);
+        float ax = fmaf(R00, p1.y, -g1.y);
+        ax = fmaf(R01, p2.x, ax);
+        ax = fmaf(R02, p2.y, ax);
+        pb += fast_sqrt(fmaf(ax, ax, fmaf(u.y, u.y, u.x * u.x)));
+      }
+      pdist = pa + pb;
+    } else {
+      // zero-extent pose: alignment undefined -> unaligned distance of the (uncentred) poses
+      const float2 T0 = sub2(MP0, MG0), T1 = sub2(MP1, MG1), T2 = sub2(MP2, MG2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 d0 = add2(sub2(P[3 * i], G[3 * i]), T0), d1 = add2(sub2(P[3 * i + 1], G[3 * i + 1]), T1),
+                     d2 = add2(sub2(P[3 * i + 2], G[3 * i + 2]), T2);
+        pdist += fast_sqrt(d0.x * d0.x + d0.y * d0.y + d1.x * d1.x);
+        pdist += fast_sqrt(d1.y * d1.y + d2.x * d2.x + d2.y * d2.y);
       }
     }
   }
@@ -391,12 +542,14 @@ constexpr int kStageBytes = 6 * kSubBytes;          // 3 groups x {pred, gt} = 4
 template <bool DO_M, bool DO_P, bool ACC>
 __global__ void __launch_bounds__(kEvalThreads, 4)
 eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_constant__ CUtensorMap tm_gt, const EvalParams prm) {
-  constexpr int J = 16, W = 48;
+  constexpr int W = 48;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   __shared__ uint64_t full;
-  __shared__ float sMean[W], sStd[W];
+  __shared__ float4 sMean4[W / 4], sStd4[W / 4];
+  float* const sMean = reinterpret_cast<float*>(sMean4);
+  float* const sStd = reinterpret_cast<float*>(sStd4);
   __shared__ ActionStage stage;
   ActionTotals tot;
   const int tid = threadIdx.x;
@@ -451,20 +604,17 @@ eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_consta
     float dist = 0.f, pdist = 0.f;
     int act = 0;
     if (valid) {
-      float P[W], G[W];
+      float2 P[24], G[24];
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
-        const int w = 4 * k;
-        P[w] = sStd[w] * pr[k].x + sMean[w];             // valid_bilinear.py:53
-        P[w + 1] = sStd[w + 1] * pr[k].y + sMean[w + 1];
-        P[w + 2] = sStd[w + 2] * pr[k].z + sMean[w + 2];
-        P[w + 3] = sStd[w + 3] * pr[k].w + sMean[w + 3];
-        G[w] = sStd[w] * gr[k].x + sMean[w];             // valid_bilinear.py:54
-        G[w + 1] = sStd[w + 1] * gr[k].y + sMean[w + 1];
-        G[w + 2] = sStd[w + 2] * gr[k].z + sMean[w + 2];
-        G[w + 3] = sStd[w + 3] * gr[k].w + sMean[w + 3];
+        const float4 sd = sStd4[k], mn = sMean4[k];
+        const float2 sd0 = f2(sd.x, sd.y), sd1 = f2(sd.z, sd.w), mn0 = f2(mn.x, mn.y), mn1 = f2(mn.z, mn.w);
+        P[2 * k] = fma2(sd0, f2(pr[k].x, pr[k].y), mn0);           // valid_bilinear.py:53
+        P[2 * k + 1] = fma2(sd1, f2(pr[k].z, pr[k].w), mn1);
+        G[2 * k] = fma2(sd0, f2(gr[k].x, gr[k].y), mn0);           // valid_bilinear.py:54
+        G[2 * k + 1] = fma2(sd1, f2(gr[k].z, gr[k].w), mn1);
       }
-      pose_metrics<J, DO_M, DO_P>(P, G, dist, pdist);
+      pose_metrics16<DO_M, DO_P>(P, G, dist, pdist);
       const int64_t gi = p0 + tid;
       if (DO_M && prm.dist_out) prm.dist_out[gi] = dist;
       if (DO_P && prm.pdist_out) prm.pdist_out[gi] = pdist;
