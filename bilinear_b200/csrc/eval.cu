@@ -4,7 +4,7 @@
 //
 // Both are HBM-bound: 2 * J * 3 * 4 bytes are read per pose (384 B at J = 16) and at most 8 bytes
 // written.  Layout of the work:
-//   - a persistent grid (4 CTAs per SM) walks chunks of 128 poses;
+//   - a persistent grid (3 CTAs per SM for the TMA-fed J = 16 kernel, 4 for the generic one) walks chunks of 128 poses;
 //   - the 128 threads of a CTA stream the chunk with 128-bit coalesced loads (24 float4 in flight per
 //     thread) into shared memory with an odd row pitch (3J+1 words -> conflict-free per-pose reads);
 //   - then ONE THREAD PER POSE pulls its 2*3J values into registers and does the whole per-pose
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams prm
 // poses} (64-byte rows, SWIZZLE_64B), so that thread r can pull ITS pose out of shared memory with
 // conflict-free 128-bit loads (unit u of row r sits at u ^ ((r >> 1) & 3)).  A CTA owns ONE 48 KB
 // buffer: as soon as every thread holds its pose in registers the buffer is handed back to the TMA
-// unit for the next chunk, which lands while the per-pose math runs -- 4 CTAs (16 warps) per SM hide
+// unit for the next chunk, which lands while the per-pose math runs -- 3 CTAs (12 warps, 168 registers each) per SM hide
 // the serial parts of the Procrustes solve, and no data passes through registers on its way into
 // shared memory.  Per-action sums: staged through shared-memory fp32 buckets (stage_add); when the caller
 // keeps no per-pose output, the in-kernel warp walk.
@@ -539,8 +539,11 @@ constexpr int kTmaPoses = kEvalThreads;             // poses per chunk
 constexpr int kSubBytes = kTmaPoses * 64;           // one 16-float column group of one tensor
 constexpr int kStageBytes = 6 * kSubBytes;          // 3 groups x {pred, gt} = 48 KB
 
+#ifndef B200_EVAL_CTAS
+#define B200_EVAL_CTAS 3   // resident CTAs per SM of the TMA-fed kernel: 3 = 168 registers, no spills (4 = 128 registers spilled 164 bytes per thread; measured 1M poses: P-MPJPE 91.2 -> 83.6 us, MPJPE 70.8 -> 67.2 us)
+#endif
 template <bool DO_M, bool DO_P, bool ACC>
-__global__ void __launch_bounds__(kEvalThreads, 4)
+__global__ void __launch_bounds__(kEvalThreads, B200_EVAL_CTAS)
 eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_constant__ CUtensorMap tm_gt, const EvalParams prm) {
   constexpr int W = 48;
   extern __shared__ uint8_t smem_raw[];
@@ -641,7 +644,7 @@ static cudaError_t launch_eval_tma_t(const EvalParams& prm, const CUtensorMap& t
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t nchunks = (prm.n + kTmaPoses - 1) / kTmaPoses;
-  const int grid = int(std::max<int64_t>(1, std::min<int64_t>(nchunks, int64_t(sms) * 4)));
+  const int grid = int(std::max<int64_t>(1, std::min<int64_t>(nchunks, int64_t(sms) * B200_EVAL_CTAS)));
   eval_kernel_tma<DO_M, DO_P, ACC><<<grid, kEvalThreads, smem, stream>>>(tp, tg, prm);
   return cudaGetLastError();
 }
