@@ -720,9 +720,11 @@ def main():
                 r["unit"] = "poses/s"
                 return compact(r)
             guarded(large)
+        # the evaluation passes (~0.1 ms each, HBM-bound) are timed BEFORE the two inference legs: those run the tensor
+        # pipe at the board's power cap for ~2 s, and the SM clock they leave behind cost the passes 10 % (round-1 verdict)
+        guarded(lambda: bench_eval(1_000_000, 50, 5, device, rank, world, peaks))
         guarded(lambda: compact(bench_infer(10_000_000, 65536, "bf16", 3, 1, device, rank, world, peaks)))
         guarded(lambda: compact(bench_infer(10_000_000, 65536, "fp32", 2, 1, device, rank, world, peaks)))
-        guarded(lambda: bench_eval(1_000_000, 50, 5, device, rank, world, peaks))
 
     torch_gpu = None
     if rank == 0 and world == 1 and not args.no_torch:     # (a single-GPU baseline: measured in the N = 1 run only)
