@@ -119,12 +119,17 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of this cluster
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of this cluster.
+// Default semantics (release at CTA scope), NOT .release.cluster: the only user hands a drained TMEM accumulator back to
+// the MMA issuer of the pair's leader CTA, which is ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync in
+// front of the arrive -- no memory written by this thread is read by the waiter.  With .release.cluster the compiler
+// emits MEMBAR.ALL.GPU + ERRBAR, i.e. the epilogue warp of the non-leader CTA sat out the acknowledgement of all its z / g
+// stores once per tile (ncu source view, profiles/r4g_*: 30 % of the samples of that warp's tile loop).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
