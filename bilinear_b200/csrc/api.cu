@@ -41,6 +41,11 @@ int eval_tma_box_rows();
 using namespace b200;
 
 // ------------------------------------------------------------------------------------------------
+#ifdef B200_EPI_TMA
+#define B200_EPI_TMA_HOST B200_EPI_TMA
+#else
+#define B200_EPI_TMA_HOST 0   // staged TMA-store epilogues are compiled out by default (mega.cu, B200_EPI_TMA)
+#endif
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
 
@@ -1121,7 +1126,7 @@ int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
   // stores of g / dy; with the apply passes split out (the default) the step time does not move either way, and the
   // epilogue-bound thin phases (K = 32 / 48) stay as long as they were -- their epilogues do not wait for the
   // load/store unit.
-  pl->tma_store = (pl->large && pl->P == 1 && !pl->helpers && !B200_BLOCKED && getenv("B200_TMA_STORE"))
+  pl->tma_store = (B200_EPI_TMA_HOST && pl->large && pl->P == 1 && !pl->helpers && !B200_BLOCKED && getenv("B200_TMA_STORE"))
                       ? (atoi(getenv("B200_TMA_STORE")) & 3) : 0;
   Carver c(desc->workspace);
   carve(c, pl->u, pl->B, pl->P, pl->kind);
