@@ -290,7 +290,6 @@ struct b200_plan {
   int sms;
   int cg = 1;                // CTAs per MMA: 2 = CTA pairs (large-batch plans), 1 otherwise
   bool split_ew = false;     // large bf16 plans: the BatchNorm apply passes run as high-occupancy kernels of their own
-  bool tma_epi_loads = false;   // large bf16 pair plans: dgrad epilogue operands through TMA staging tiles (Args::tm_z / tm_s)
   int tma_store = 0;         // large bf16 plans: epilogue rows leave through shared-memory staging tiles + TMA stores
                              // (bit 0: forward z, bit 1: dgrad g / dy)
   bool helpers = false;      // CTA pairs + helper warps: apply passes overlap the GEMM that consumes them (mega_pairx.cu)
@@ -337,8 +336,6 @@ static int end_phase(b200_plan* pl) {
   int ring = mega_ring_bytes();
   for (int j = 0; j < p.num_gemm; ++j)
     if (pl->cur.gj[j].a.tm_out) ring = mega_ring_bytes() - kEpiStageBytes;   // epilogue staging tiles sit at the top
-  for (int j = 0; j < p.num_gemm; ++j)
-    if (pl->cur.gj[j].a.tm_z) ring = mega_ring_bytes() - kEpiLoadBytes;      // ... or the epilogue's load ring
   p.num_stages = std::max(1, std::min(8, ring / sb));
   p.aux_off = -1;
   if (pl->helpers && p.num_ew > 0) {
@@ -485,21 +482,6 @@ static int add_gemm(b200_plan* pl, const PlaneRef& A, int a_mn, const PlaneRef& 
     if (encode_out_map(&m, dst, a.ldT, M, a.ldT)) return 1;
     pl->tm.push_back(m);
     g.a.tm_out = pl->u.tmaps + (pl->tm.size() - 1);
-  }
-  g.a.tm_z = g.a.tm_s = nullptr;
-  if (pl->tma_epi_loads && !g.a.tm_out && a.planes == 1 && M % 128 == 0 && epi == EPI_DGRAD_LARGE && a.stats != nullptr &&
-      a.zT != nullptr) {
-    // the epilogue's z / residual-gradient rows arrive through the TMA unit (Args::tm_z, tm_s)
-    const void* src[2] = {a.zT, a.skip_in};
-    const void** dst[2] = {&g.a.tm_z, &g.a.tm_s};
-    for (int i = 0; i < 2; ++i) {
-      if (!src[i]) continue;
-      if (int(pl->tm.size()) >= kMaxTmaps) return fail("too many tensor maps");
-      CUtensorMap m;
-      if (encode_out_map(&m, src[i], a.ldT, M, a.ldT)) return 1;
-      pl->tm.push_back(m);
-      *dst[i] = pl->u.tmaps + (pl->tm.size() - 1);
-    }
   }
   pl->cur.gj[pl->cur.ph.num_gemm++] = g;
   return 0;
@@ -1144,8 +1126,6 @@ int b200_plan_create(const b200_plan_desc* desc, b200_plan** out) {
   // stores of g / dy; with the apply passes split out (the default) the step time does not move either way, and the
   // epilogue-bound thin phases (K = 32 / 48) stay as long as they were -- their epilogues do not wait for the
   // load/store unit.
-  pl->tma_epi_loads = pl->large && pl->P == 1 && !pl->helpers && !B200_BLOCKED &&
-                      !(getenv("B200_EPI_TMALD") && atoi(getenv("B200_EPI_TMALD")) == 0);
   pl->tma_store = (B200_EPI_TMA_HOST && pl->large && pl->P == 1 && !pl->helpers && !B200_BLOCKED && getenv("B200_TMA_STORE"))
                       ? (atoi(getenv("B200_TMA_STORE")) & 3) : 0;
   Carver c(desc->workspace);

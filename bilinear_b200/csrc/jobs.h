@@ -211,17 +211,8 @@ struct alignas(16) Args {
   // epilogue thread owns one feature row: its 64-byte runs go through a shared-memory staging tile and out with
   // ONE TMA store per warp and chunk instead of 32 two-sector requests through the load/store unit.  nullptr: direct stores.
   const void* tm_out;
-  // ---- EPI_DGRAD_LARGE, bf16: tensor maps (same geometry) of the two feature-major tensors the epilogue READS -- the
-  // saved pre-BatchNorm z and the gradient arriving over the residual edge.  An epilogue thread owns one feature row, so
-  // a warp-wide global load of these rows touches 32 different 128-byte lines for 32 bytes each; with the maps the
-  // warp's 32 x 64-byte blocks come in through the TMA unit (a ring of kEpiLdStages staging tiles per warp, mbarrier
-  // per tile) and every lane pulls its row out of shared memory with four conflict-free 128-bit loads.  nullptr: direct loads.
-  const void* tm_z;
-  const void* tm_s;
 };
 constexpr int kEpiStageBytes = 16 * 1024;   // 4 epilogue warps x 2 staging tiles x 2 KB, at the top of the ring region
-constexpr int kEpiLdStages = 3;                              // staging tiles (z + residual: 4 KB) per epilogue warp
-constexpr int kEpiLoadBytes = 4 * kEpiLdStages * 4096;       // 48 KB at the top of the ring region (never together with tm_out)
 
 struct alignas(16) GemmJob {
   int32_t tmap_a, tmap_b;  // indices into the tensor-map table
