@@ -68,6 +68,30 @@ def test_known_answers(cuda_lib):
     assert np.abs(rm.pdist.double().cpu().numpy() - ref).max() / 16 < TOL_MM
 
 
+def test_large_rotations_both_adjugate_paths(cuda_lib):
+    """The kernel takes the optimal quaternion from the FIRST column of the adjugate when q0^2 > 0.1 (turns below ~143
+    degrees) and from the full pivoted adjugate otherwise (eval.cu, horn_top): sweep the turn angle across that boundary up
+    to 180 degrees, about random axes, with noise, and compare with the float64 oracle."""
+    rng = np.random.default_rng(5)
+    n = 4096
+    G = 200.0 * rng.standard_normal((n, 16, 3))
+    axis = rng.standard_normal((n, 3))
+    axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+    ang = np.linspace(np.deg2rad(100.0), np.pi, n)
+    K = np.zeros((n, 3, 3))
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0] = -axis[:, 2], axis[:, 1], axis[:, 2]
+    K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -axis[:, 0], -axis[:, 1], axis[:, 0]
+    R = np.eye(3)[None] + np.sin(ang)[:, None, None] * K + (1.0 - np.cos(ang))[:, None, None] * (K @ K)   # Rodrigues
+    P = 0.8 * (G @ R) + 25.0 * rng.standard_normal((n, 1, 3)) + 10.0 * rng.standard_normal((n, 16, 3))
+    g32 = G.reshape(n, -1).astype(np.float32)
+    p32 = P.reshape(n, -1).astype(np.float32)
+    dev = torch.device("cuda")
+    r = metrics.evaluate(torch.from_numpy(p32).to(dev), torch.from_numpy(g32).to(dev), None, None, None, 1, joints=16)
+    ref = pm.pmpjpe_per_pose_torch(p32, g32)
+    assert np.isfinite(r.pdist.cpu().numpy()).all()
+    assert np.abs(r.pdist.double().cpu().numpy() - ref).max() / 16 < TOL_MM
+
+
 def test_degenerate_poses_finite(cuda_lib):
     rng = np.random.default_rng(1)
     G = (100.0 * rng.standard_normal((8, 16, 3))).astype(np.float32)
