@@ -399,25 +399,37 @@ __device__ __forceinline__ void pose_metrics16(float2* P, float2* G, float& dist
 // atomic exchange (read-and-clear: an add that arrives later simply stays for the next round).  The float64 totals
 // leave the CTA once, at the end.  This replaced (i) a second kernel re-reading the per-pose results (11-18 us of
 // kernel plus ~18 us of launch gap on a 62 us pass) and (ii) warp-shuffle reductions per bucket (+24-29 us).
+// Buckets are FIXED-POINT (1/256 mm) unsigned 32-bit counters: a 32-bit integer add is a native shared-memory atomic, a float
+// add is a compare-and-swap loop (ncu, r4x: 8 trips per warp with 15 actions, 7 % of the P-MPJPE kernel's samples).  A bucket
+// holds at most two chunks (256 poses: the collecting thread may be overtaken by early adds of the next chunk) before it
+// is cleared, so per-pose values below kFixMax cannot overflow it; anything larger (metres of error per joint) goes to
+// the float buckets through the slow path.  Rounding: <= 1/512 mm per pose, unbiased -- three orders of magnitude below the
+// 0.05 mm tolerance of the per-action means.
+constexpr float kFixScale = 256.0f, kFixMax = 4.0e4f;   // 256 poses x 4e4 mm x 256 = 2.6e9 < 2^32
 struct ActionStage {
-  float s[kMaxActions], ps[kMaxActions];
+  unsigned int s[kMaxActions], ps[kMaxActions];
+  float sf[kMaxActions], psf[kMaxActions];
   unsigned int c[kMaxActions];
 };
 struct ActionTotals {
   double s = 0.0, ps = 0.0;
   unsigned long long c = 0ull;
 };
+__device__ __forceinline__ void stage_add1(unsigned int* fix, float* flt, int act, float v) {
+  if (v < kFixMax) atomicAdd(&fix[act], __float2uint_rn(v * kFixScale));   // (negative / NaN never happen: sums of square roots)
+  else atomicAdd(&flt[act], v);
+}
 template <bool DO_M, bool DO_P>
 __device__ __forceinline__ void stage_add(ActionStage& st, int act, float dist, float pdist) {
-  if (DO_M) atomicAdd(&st.s[act], dist);
-  if (DO_P) atomicAdd(&st.ps[act], pdist);
+  if (DO_M) stage_add1(st.s, st.sf, act, dist);
+  if (DO_P) stage_add1(st.ps, st.psf, act, pdist);
   atomicAdd(&st.c[act], 1u);
 }
 template <bool DO_M, bool DO_P>
 __device__ __forceinline__ void stage_collect(ActionStage& st, ActionTotals& tot, int tid, int n_actions) {
   if (tid < n_actions) {
-    if (DO_M) tot.s += double(atomicExch(&st.s[tid], 0.f));
-    if (DO_P) tot.ps += double(atomicExch(&st.ps[tid], 0.f));
+    if (DO_M) tot.s += double(atomicExch(&st.s[tid], 0u)) * (1.0 / double(kFixScale)) + double(atomicExch(&st.sf[tid], 0.f));
+    if (DO_P) tot.ps += double(atomicExch(&st.ps[tid], 0u)) * (1.0 / double(kFixScale)) + double(atomicExch(&st.psf[tid], 0.f));
     tot.c += atomicExch(&st.c[tid], 0u);
   }
 }
@@ -445,7 +457,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams prm
   __shared__ ActionStage stage;
   ActionTotals tot;
   const int tid = threadIdx.x;
-  for (int i = tid; i < kMaxActions; i += CH) { stage.s[i] = 0.f; stage.ps[i] = 0.f; stage.c[i] = 0u; }
+  for (int i = tid; i < kMaxActions; i += CH) { stage.s[i] = 0u; stage.ps[i] = 0u; stage.sf[i] = 0.f; stage.psf[i] = 0.f; stage.c[i] = 0u; }
   const bool unnorm = prm.mean != nullptr;
   for (int i = tid; i < W; i += CH) {
     sMean[i] = unnorm ? prm.mean[i] : 0.f;
@@ -556,7 +568,9 @@ eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_consta
   __shared__ ActionStage stage;
   ActionTotals tot;
   const int tid = threadIdx.x;
-  for (int i = tid; i < kMaxActions; i += kEvalThreads) { stage.s[i] = 0.f; stage.ps[i] = 0.f; stage.c[i] = 0u; }
+  for (int i = tid; i < kMaxActions; i += kEvalThreads) {
+    stage.s[i] = 0u; stage.ps[i] = 0u; stage.sf[i] = 0.f; stage.psf[i] = 0.f; stage.c[i] = 0u;
+  }
   const bool unnorm = prm.mean != nullptr;
   for (int i = tid; i < W; i += kEvalThreads) {
     sMean[i] = unnorm ? prm.mean[i] : 0.f;
@@ -581,6 +595,10 @@ eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_consta
   if (tid == 0 && int64_t(blockIdx.x) < nchunks) issue(blockIdx.x);
   uint32_t parity = 0;
   for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, parity ^= 1u) {
+    // this pose's action id: requested BEFORE the chunk is waited for -- read where it is used (after the per-pose math) the
+    // load sat out a full DRAM round trip per chunk: 25 % of the P-MPJPE kernel's stall samples (ncu source view, r4x)
+    int act = 0;
+    if (ACC && prm.action && ch * kTmaPoses + tid < prm.n) act = __ldg(prm.action + ch * kTmaPoses + tid);
     mbar_wait(&full, parity, 900);
     float4 pr[12], gr[12];
     {
@@ -605,7 +623,6 @@ eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_consta
     const int np = int(min(int64_t(kTmaPoses), prm.n - p0));
     const bool valid = tid < np;
     float dist = 0.f, pdist = 0.f;
-    int act = 0;
     if (valid) {
       float2 P[24], G[24];
 #pragma unroll
@@ -622,7 +639,6 @@ eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_consta
       if (DO_M && prm.dist_out) prm.dist_out[gi] = dist;
       if (DO_P && prm.pdist_out) prm.pdist_out[gi] = pdist;
       if (ACC) {
-        act = prm.action ? prm.action[gi] : 0;
         act = min(max(act, 0), prm.n_actions - 1);
         stage_add<DO_M, DO_P>(stage, act, dist, pdist);
       }
