@@ -613,18 +613,16 @@ eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_consta
         }
       }
     }
-    __syncthreads();   // every thread holds its pose: the buffer goes back to the TMA unit
-    if (ACC) stage_collect<DO_M, DO_P>(stage, tot, tid, prm.n_actions);   // (the previous chunk's adds are all in)
-    if (tid == 0 && ch + gridDim.x < nchunks) {
-      fence_proxy_async_all();
-      issue(ch + gridDim.x);
-    }
-    const int64_t p0 = ch * kTmaPoses;
-    const int np = int(min(int64_t(kTmaPoses), prm.n - p0));
-    const bool valid = tid < np;
-    float dist = 0.f, pdist = 0.f;
-    if (valid) {
-      float2 P[24], G[24];
+    // Un-normalise BEFORE the barrier: the arithmetic consumes every value the 24 shared-memory loads above deliver, so a
+    // thread that arrives at the barrier has its reads of the buffer behind it -- and the TMA write of the next chunk, issued
+    // right after the barrier, cannot overtake them.  That is what lets the re-issue go without fence.proxy.async (the reads
+    // are done, and nothing was WRITTEN to the buffer through the generic proxy): the fence + MEMBAR.ALL.CTA in front of the
+    // issue were 20 % of the issuing warp's samples (r4y), i.e. time the buffer sat idle in a pass that waits for HBM.
+    // (MPJPE alone has almost no math behind the barrier: there the short path to the re-issue is loads -> barrier -> fence,
+    // and the un-normalisation follows -- measured 66 us against 70 us with the order below)
+    constexpr bool kEarly = DO_P;
+    float2 P[24], G[24];
+    auto unnormalise = [&]() {
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
         const float4 sd = sStd4[k], mn = sMean4[k];
@@ -634,6 +632,20 @@ eval_kernel_tma(const __grid_constant__ CUtensorMap tm_pred, const __grid_consta
         G[2 * k] = fma2(sd0, f2(gr[k].x, gr[k].y), mn0);           // valid_bilinear.py:54
         G[2 * k + 1] = fma2(sd1, f2(gr[k].z, gr[k].w), mn1);
       }
+    };
+    if (kEarly) unnormalise();
+    __syncthreads();   // every thread holds its pose: the buffer goes back to the TMA unit
+    if (tid == 0 && ch + gridDim.x < nchunks) {
+      if (!kEarly) fence_proxy_async_all();
+      issue(ch + gridDim.x);
+    }
+    if (ACC) stage_collect<DO_M, DO_P>(stage, tot, tid, prm.n_actions);   // (the previous chunk's adds are all in)
+    if (!kEarly) unnormalise();
+    const int64_t p0 = ch * kTmaPoses;
+    const int np = int(min(int64_t(kTmaPoses), prm.n - p0));
+    const bool valid = tid < np;
+    float dist = 0.f, pdist = 0.f;
+    if (valid) {
       pose_metrics16<DO_M, DO_P>(P, G, dist, pdist);
       const int64_t gi = p0 + tid;
       if (DO_M && prm.dist_out) prm.dist_out[gi] = dist;
