@@ -483,6 +483,12 @@ static int add_gemm(b200_plan* pl, const PlaneRef& A, int a_mn, const PlaneRef& 
     pl->tm.push_back(m);
     g.a.tm_out = pl->u.tmaps + (pl->tm.size() - 1);
   }
+  // large bf16 wgrad K-slices: the vector reductions leave through the epilogue warps' staging tiles (mega.cu, epi_wgrad);
+  // tm_out is only a FLAG here (it also makes end_phase keep the staging region out of the operand ring)
+  static const bool wgrad_stage_off = getenv("B200_WGRAD_STAGE") && atoi(getenv("B200_WGRAD_STAGE")) == 0;   // A/B switch
+  if (epi == EPI_WGRAD && pl->large && a.planes == 1 && g.ksplit > 1 && M % (128 * cg) == 0 && N % 32 == 0 && !pl->helpers &&
+      !wgrad_stage_off)
+    g.a.tm_out = pl->u.tmaps;
   pl->cur.gj[pl->cur.ph.num_gemm++] = g;
   return 0;
 }
