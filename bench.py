@@ -43,7 +43,7 @@ SPACER_CYCLES = 600_000                     # ~0.3 ms at 1.9 GHz
 EVAL_BYTES_PER_POSE = 384                   # 2 x 16 x 3 x 4 bytes read per pose
 LARGE_BATCH = 65536
 CPU_SAMPLE_ROWS = 8192                      # rows of the 65 536-row step the CPU arm times per step (bounded sample)
-NCU_TRAFFIC = {"train_b65536": "r4p_train_step_b65536_bf16_ncu.csv", "train_b64": "r1p_train_step_b64_fp32_ncu_full.csv"}
+NCU_TRAFFIC = {"train_b65536": "r5_train_step_b65536_bf16_ncu.csv", "train_b64": "r1p_train_step_b64_fp32_ncu_full.csv"}
 
 
 def ncu_traffic(name):
@@ -349,7 +349,7 @@ def bench_train(precision, batch, steps, warmup, device, world, peaks, with_e2e=
                                traffic=ncu_traffic(NCU_TRAFFIC["train_b65536"]) if batch == LARGE_BATCH else None,
                                peak_source=peaks["source"] + " (cuBLAS bf16 8192^3: burst %.0f, sustained %.0f TFLOP/s)"
                                % (peaks["bf16"], peaks["bf16_sustained"]),
-                               traffic_note="DRAM bytes of ONE step = its 22 launches together (ncu, profiles/r4p_train_step_"
+                               traffic_note="DRAM bytes of ONE step = its 22 launches together (ncu, profiles/r5_train_step_"
                                             "b65536_bf16_launch_list.txt); algorithmic activation traffic ~4.6 GB" if batch == LARGE_BATCH
                                else None,
                                algorithmic="25 591 808 FLOP/pose x %d poses per step per GPU" % batch)
