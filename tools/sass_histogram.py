@@ -28,7 +28,7 @@ def main():
             name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
             cur = per.setdefault(re.sub(r"\(.*", "", name), collections.Counter())
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if m and cur is not None:
             op = m.group(1)
             cur["total"] += 1
