@@ -13,7 +13,7 @@
 //     characteristic quartic (the QCP method), eigenvector from the adjugate -- scale, aligned
 //     distances.  Degenerate poses (repeated top eigenvalue, zero extent) fall back to a cyclic
 //     Jacobi eigen-solver / the unaligned distance, so the result is always finite.
-//   - per-action sums are staged in fp32 shared-memory buckets per chunk, collected into fp64 per-CTA totals and
+//   - per-action sums are staged in fixed-point (1/256 mm) shared-memory buckets per chunk, collected into fp64 per-CTA totals and
 //     flushed with one double atomic per action per CTA.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -395,7 +395,7 @@ __device__ __forceinline__ void pose_metrics16(float2* P, float2* G, float& dist
 // Per-action accumulation (valid_bilinear.py:61-70) staged through shared memory.  Every pose adds its two fp32
 // results and a count to the CTA's staging buckets with native shared-memory atomics (3 instructions per pose, a
 // few-way conflict among the 32 lanes); once per chunk, right behind the barrier the chunk loop has anyway, thread a
-// moves bucket a -- the fp32 sum of at most a couple of hundred values -- into its float64 accumulator with an
+// moves bucket a -- the fixed-point sum of at most a couple of hundred values -- into its float64 accumulator with an
 // atomic exchange (read-and-clear: an add that arrives later simply stays for the next round).  The float64 totals
 // leave the CTA once, at the end.  This replaced (i) a second kernel re-reading the per-pose results (11-18 us of
 // kernel plus ~18 us of launch gap on a 62 us pass) and (ii) warp-shuffle reductions per bucket (+24-29 us).
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams prm
 // buffer: as soon as every thread holds its pose in registers the buffer is handed back to the TMA
 // unit for the next chunk, which lands while the per-pose math runs -- 3 CTAs (12 warps, 168 registers each) per SM hide
 // the serial parts of the Procrustes solve, and no data passes through registers on its way into
-// shared memory.  Per-action sums: staged through shared-memory fp32 buckets (stage_add); when the caller
+// shared memory.  Per-action sums: staged through fixed-point shared-memory buckets (stage_add); when the caller
 // keeps no per-pose output, the in-kernel warp walk.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTmaPoses = kEvalThreads;             // poses per chunk
